@@ -1,0 +1,85 @@
+"""Loads libjxlb200.so and declares the C ABI of include/jxlb200.h for ctypes.
+
+There is no CPU fallback: if the library is missing it is built with nvcc (jxlatte_b200/build.py); if that fails, or
+the library cannot be loaded, importing the product path raises.
+"""
+import ctypes as C
+import os
+
+from .params import FrameParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libjxlb200.so")
+
+OK, E_ARG, E_STREAM, E_UNSUPPORTED, E_CUDA = 0, -1, -2, -3, -4
+QM_FLOATS = 3 * 131584
+HALO_ROWS = 8
+
+
+class QmParams(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("n_dct", C.c_int32), ("n_param", C.c_int32), ("n_4x4", C.c_int32),
+        ("denominator", C.c_float),
+        ("dct_param", (C.c_float * 17) * 3), ("param", (C.c_float * 9) * 3), ("params4x4", (C.c_float * 17) * 3),
+        ("raw", C.POINTER(C.c_float) * 3),
+    ]
+
+
+class Slab(C.Structure):
+    _fields_ = [("y0", C.c_int32), ("rows", C.c_int32), ("frame_height", C.c_int32),
+                ("has_top", C.c_int32), ("has_bottom", C.c_int32)]
+
+
+# every symbol include/jxlb200.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+_i32 = C.c_int32
+_P3 = C.POINTER(_vp)   # const T *const planes[3]
+_FP = C.POINTER(FrameParams)
+SYMBOLS = {
+    "jxlb200_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "jxlb200_destroy": (None, [_vp]),
+    "jxlb200_last_error": (C.c_char_p, [_vp]),
+    "jxlb200_set_stream": (_i32, [_vp, _vp]),
+    "jxlb200_sync": (_i32, [_vp]),
+    "jxlb200_launch_count": (C.c_int64, [_vp]),
+    "jxlb200_qm_default_params": (_i32, [C.POINTER(QmParams)]),
+    "jxlb200_qm_generate": (_i32, [C.POINTER(QmParams), _vp, _vp]),
+    "jxlb200_set_qm_weights": (_i32, [_vp, _vp, _vp]),
+    "jxlb200_vardct_reconstruct": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
+    "jxlb200_vardct_invert_dev": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _P3, C.c_int64]),
+    "jxlb200_restore_dev": (_i32, [_vp, _FP, C.POINTER(Slab), _P3, C.c_int64, _vp, _vp, _P3]),
+    "jxlb200_vardct_reconstruct_dev": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
+    "jxlb200_gaborish": (_i32, [_vp, _FP, _P3, _P3]),
+    "jxlb200_epf": (_i32, [_vp, _FP, _P3, _vp, _vp, _P3]),
+    "jxlb200_color_transform": (_i32, [_vp, _FP, _P3, _P3]),
+    "jxlb200_vardct_invert": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _P3]),
+    "jxlb200_modular_rct": (_i32, [_vp, _P3, _i32, _i32, _i32]),
+    "jxlb200_modular_palette": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _P3]),
+    "jxlb200_modular_squeeze": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "jxlb200_modular_rct_dev": (_i32, [_vp, _P3, _i32, _i32, _i32]),
+    "jxlb200_modular_palette_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _P3]),
+    "jxlb200_modular_squeeze_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """The loaded library.  Raises if it cannot be built or loaded (no silent fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            from . import build
+            build.build()
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)   # AttributeError here = header and library drifted apart
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def planes(ptrs):
+    """int/ctypes pointers -> `const T *const p[n]` argument."""
+    return (_vp * len(ptrs))(*[_vp(int(p)) if not isinstance(p, _vp) else p for p in ptrs])

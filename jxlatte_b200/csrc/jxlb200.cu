@@ -1,0 +1,702 @@
+// jxlb200.cu -- libjxlb200.so: context, buffers and the C ABI declared in include/jxlb200.h.
+// Single translation unit (all kernels are included here) so __constant__ tables need no relocatable device code.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+#include "k0_lists.cuh"
+#include "k1_idct.cuh"
+#include "k2_restore.cuh"
+#include "k2_fused.cuh"
+#include "k3_modular.cuh"
+#include "qm_tables.cuh"
+
+// grow-only device allocation
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct jxlb200_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    bool have_weights = false;
+
+    DevBuf sched, items, gate, wraw, woff, wexp, lut8, sigma, flags;
+    DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
+    DevBuf pp[2];      // ping-pong planes of the staged stage 2
+    DevBuf in_q, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    DevTables tab;
+
+    int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+        err = what;
+        if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+        return code;
+    }
+};
+
+namespace {
+
+const float kAfvBasis[256] = {
+#include "afv_basis.inc"
+};
+const float kScaleF[32] = {
+    1.0000000000000000000f, 1.0003954307206444720f, 1.0015830492063566798f, 1.0035668445359847378f, 1.0063534990068075448f,
+    1.0099524393750471170f, 1.0143759095929498827f, 1.0196390660646908181f, 1.0257600967811994622f, 1.0327603660498609462f,
+    1.0406645869479269795f, 1.0495010240726261235f, 1.0593017296818027804f, 1.0701028169146909598f, 1.0819447744633102634f,
+    1.0948728278735071820f, 1.1089373535928257701f, 1.1241943530045446156f, 1.1407059950032801390f, 1.1585412372562662921f,
+    1.1777765381971696030f, 1.1984966740821024139f, 1.2207956782314713353f, 1.2447779229495839992f, 1.2705593687655135089f,
+    1.2982690107340108228f, 1.3280505578212198723f, 1.3600643892400108061f, 1.3944898413648201160f, 1.4315278911623840964f,
+    1.4714043176060183528f, 1.5143734423313919909f,
+};
+
+template <int N, int PASS> cudaError_t big_attr() {
+    return cudaFuncSetAttribute(k1_big<N, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigSmem<N>::kBytes);
+}
+
+int upload_constants(jxlb200_ctx *ctx) {
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_tt, h_tt, sizeof(h_tt)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_small_types, h_small_types, sizeof(h_small_types)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_med_types, h_med_types, sizeof(h_med_types)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_big_types, h_big_types, sizeof(h_big_types)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_afv, kAfvBasis, sizeof(kAfvBasis)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_llf_scale, kScaleF, sizeof(kScaleF)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec64, h_sec64, sizeof(h_sec64)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec128, h_sec128, sizeof(h_sec128)));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec256, h_sec256, sizeof(h_sec256)));
+    // MathHelper.cosineLut (J/util/MathHelper.java:19-30): (float)(sqrt2 * cos(pi (n+1) (k+0.5) / s)), double math
+    float cosv[1302];
+    int offs[6] = {0, 0, 0, 0, 0, 0}, o = 0;
+    const double root2 = sqrt(2.0);
+    for (int l = 1; l <= 5; l++) {
+        const int s = 1 << l;
+        offs[l] = o;
+        for (int n = 0; n < s - 1; n++)
+            for (int k = 0; k < s; k++) cosv[o++] = (float)(root2 * cos(M_PI * (n + 1) * (k + 0.5) / s));
+    }
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_cos, cosv, sizeof(float) * o));
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_cos_off, offs, sizeof(offs)));
+    int wo = 0;
+    for (int t = 0; t < 27; t++) { ctx->tab.wexp_off[t] = wo; wo += 3 * h_tt[t].bh * h_tt[t].bw * 64; }
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_tab, &ctx->tab, sizeof(DevTables)));
+    CUDA_TRY(ctx, ctx->wexp.ensure(sizeof(float) * wo));
+    CUDA_TRY(ctx, (big_attr<32, 0>()));  CUDA_TRY(ctx, (big_attr<64, 0>()));
+    CUDA_TRY(ctx, (big_attr<128, 0>())); CUDA_TRY(ctx, (big_attr<256, 0>()));
+    CUDA_TRY(ctx, (big_attr<32, 1>()));  CUDA_TRY(ctx, (big_attr<64, 1>()));
+    CUDA_TRY(ctx, (big_attr<128, 1>())); CUDA_TRY(ctx, (big_attr<256, 1>()));
+    return k2_fused_init(ctx);
+}
+
+int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!p) return ctx->fail(JXLB200_E_ARG, "frame params are NULL");
+    if (p->width <= 0 || p->height <= 0 || (p->width & 7) || (p->height & 7))
+        return ctx->fail(JXLB200_E_ARG, "padded frame size must be positive multiples of 8");
+    if (p->width > 65535 * 8 || p->height > 65535 * 8) return ctx->fail(JXLB200_E_ARG, "frame too large");
+    for (int c = 0; c < 3; c++)
+        if (p->shift_x[c] || p->shift_y[c])
+            return ctx->fail(JXLB200_E_UNSUPPORTED, "chroma subsampling (jpegUpsampling != 0) is not implemented in this build");
+    if (p->epf_iters < 0 || p->epf_iters > 3) return ctx->fail(JXLB200_E_ARG, "epf_iters outside 0..3");
+    if (p->global_scale == 0) return ctx->fail(JXLB200_E_ARG, "global_scale is 0");
+    return 0;
+}
+
+template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls) {
+    const int per_sm = N >= 128 ? 1 : (N == 64 ? 2 : 4);
+    k1_big<N, PASS><<<ctx->sms * per_sm, 384, BigSmem<N>::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
+    ctx->launches++;
+}
+
+// stage 1 on device pointers
+int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *const q[3], const float *const lf[3],
+               const uint8_t *ds, const uint8_t *bo, const int32_t *hf_mul, const int32_t *xfy, const int32_t *bfy,
+               float *const out[3], long long pitch) {
+    if (!ctx->have_weights) return ctx->fail(JXLB200_E_ARG, "jxlb200_set_qm_weights has not been called");
+    const int W = p->width, H = p->height, wb = W >> 3, hb = H >> 3, tw = (W + 63) >> 6, th = (H + 63) >> 6;
+    CUDA_TRY(ctx, ctx->sched.ensure(sizeof(Sched)));
+    CUDA_TRY(ctx, ctx->items.ensure(sizeof(int) * (size_t)wb * hb));
+    CUDA_TRY(ctx, ctx->gate.ensure(sizeof(int) * (size_t)tw * th));
+    cudaStream_t st = ctx->stream;
+    Sched *S = ctx->sched.as<Sched>();
+    CUDA_TRY(ctx, cudaMemsetAsync(S, 0, sizeof(Sched), st));
+    const int ncells = wb * hb;
+    const int g0 = min(ctx->sms * 4, ceil_div(ncells, 256));
+    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, S);
+    k0_plan<<<1, 32, 0, st>>>(S);
+    k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>());
+    k0_cfl_gate<<<ceil_div(tw * th, 128), 128, 0, st>>>(ds, bo, hb, wb, th, tw, ctx->gate.as<int>());
+    ctx->launches += 4;
+
+    K1Params P;
+    for (int c = 0; c < 3; c++) { P.q[c] = q[c]; P.lf[c] = lf[c]; P.out[c] = out[c]; }
+    P.out_pitch = pitch;
+    P.dct_select = ds; P.hf_mul = hf_mul; P.xfy = xfy; P.bfy = bfy;
+    P.cfl_gate = ctx->gate.as<int>();
+    P.wexp = ctx->wexp.as<float>();
+    P.W = W; P.H = H; P.wb = wb; P.hb = hb; P.tw = tw;
+    // HFCoefficients.dequantizeHFCoefficients :270-275
+    const float gs = 65536.0f / p->global_scale;
+    P.sf[0] = gs * (float)pow(0.8, p->xqm_scale - 2.0);
+    P.sf[1] = gs;
+    P.sf[2] = gs * (float)pow(0.8, p->bqm_scale - 2.0);
+    for (int c = 0; c < 3; c++) P.qb[c] = p->quant_bias[c];
+    P.qbn = p->quant_bias_numerator;
+    P.base_x = p->base_corr_x; P.base_b = p->base_corr_b; P.color_factor = (float)p->color_factor;
+
+    k1_small<<<min(ctx->sms * 8, ceil_div(ncells, SMALL_BATCH)), 128, 0, st>>>(P, S, ctx->items.as<int>());
+    k1_medium<<<min(ctx->sms * 4, ceil_div(ncells, 2)), 256, 0, st>>>(P, S, ctx->items.as<int>());
+    ctx->launches += 2;
+    launch_big<32, 0>(ctx, P, 0); launch_big<64, 0>(ctx, P, 1); launch_big<128, 0>(ctx, P, 2); launch_big<256, 0>(ctx, P, 3);
+    launch_big<32, 1>(ctx, P, 0); launch_big<64, 1>(ctx, P, 1); launch_big<128, 1>(ctx, P, 2); launch_big<256, 1>(ctx, P, 3);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+void fill_k2(K2Params &K, const jxlb200_frame_params *p, const jxlb200_slab *slab) {
+    memset(&K, 0, sizeof(K));
+    K.W = p->width;
+    K.rows = slab ? slab->rows : p->height;
+    K.y0 = slab ? slab->y0 : 0;
+    K.frame_h = slab ? slab->frame_height : p->height;
+    K.has_top = slab ? slab->has_top : 0;
+    K.has_bottom = slab ? slab->has_bottom : 0;
+    K.wb = p->width >> 3;
+    K.gab = p->gab; K.iters = p->epf_iters; K.color_mode = p->color_mode;
+    for (int c = 0; c < 3; c++) {   // Frame.performGabConvolution :510-517
+        const float w1 = p->gab_w1[c], w2 = p->gab_w2[c];
+        const float mult = 1.0f / (1.0f + 4.0f * (w1 + w2));
+        K.gab_base[c] = mult; K.gab_adj[c] = w1 * mult; K.gab_diag[c] = w2 * mult;
+        K.ch_scale[c] = p->epf_channel_scale[c];
+    }
+    K.gscale = 65536.0f / p->global_scale;
+    for (int i = 0; i < 8; i++) K.sharp_lut[i] = p->epf_sharp_lut[i];
+    const float step = 1.65f * 4.0f * (1.0f - (float)sqrt(0.5));   // Frame.java:545
+    K.sigma_scale[0] = step * p->epf_pass0_sigma_scale;
+    K.sigma_scale[1] = step;
+    K.sigma_scale[2] = step * p->epf_pass2_sigma_scale;
+    K.border_mul = p->epf_border_sad_mul;
+    const float it = 255.0f / p->intensity_target;                    // OpsinInverseMatrix.invertXYB :108-119
+    for (int i = 0; i < 9; i++) K.m[i] = p->opsin_matrix[i] * it;
+    for (int c = 0; c < 3; c++) { K.ob[c] = p->opsin_bias[c]; K.cob[c] = -(float)cbrt((double)p->opsin_bias[c]); }
+}
+
+// stage 2 on device pointers
+int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_slab *slab, const float *const xyb[3],
+                long long pitch, const int32_t *hf_mul, const int32_t *sharp, float *const out[3]) {
+    K2Params K;
+    fill_k2(K, p, slab);
+    const int W = K.W, rows = K.rows, wb = K.wb;
+    if (slab && ((slab->y0 & 255) || (slab->rows & 7) || slab->rows <= 0 || slab->y0 + slab->rows > slab->frame_height))
+        return ctx->fail(JXLB200_E_ARG, "slab must start on a group row and stay inside the frame");
+    cudaStream_t st = ctx->stream;
+    for (int c = 0; c < 3; c++) { K.in[c] = xyb[c]; K.out[c] = out[c]; }
+    K.in_pitch = pitch; K.out_pitch = W;
+    K.hf_mul = hf_mul; K.sharpness = sharp;
+
+    // inverse sigma per block, with one extra block row towards each neighbour slab
+    float *inv_sigma = nullptr;
+    if (K.iters > 0) {
+        CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * (rows / 8 + 2)));
+        CUDA_TRY(ctx, ctx->lut8.ensure(sizeof(float) * 8));
+        CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->lut8.p, K.sharp_lut, sizeof(float) * 8, cudaMemcpyHostToDevice, st));
+        inv_sigma = ctx->sigma.as<float>() + wb;
+        const int br0 = K.has_top ? -1 : 0, br1 = rows / 8 + (K.has_bottom ? 1 : 0);
+        k2_sigma<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(hf_mul, sharp, wb, br0, br1, K.gscale,
+                                                                                     ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
+        ctx->launches++;
+    }
+    if (k2_fused_supported(K)) {
+        int rc = k2_fused_launch(ctx, K, inv_sigma);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    }
+
+    // ---- staged fallback-free path: one kernel per stage, planes ping-pong through ctx->pp ----
+    const long long pp_pitch = W;
+    const size_t plane = (size_t)(rows + 2 * JXLB200_HALO_ROWS) * W;
+    int reach[4], n_epf = 0, pass_id[3];
+    if (K.iters == 3) pass_id[n_epf++] = 0;
+    if (K.iters >= 1) pass_id[n_epf++] = 1;
+    if (K.iters >= 2) pass_id[n_epf++] = 2;
+    static const int kReach[3] = {3, 2, 1};
+    // reach[i] = rows of margin stage i's output still needs for the stages after it
+    int acc = 0;
+    for (int i = n_epf - 1; i >= 0; i--) { reach[i + 1] = acc; acc += kReach[pass_id[i]]; }
+    reach[0] = acc;   // margin needed on the Gaborish output (or on the input if gab is off)
+    const float *cur[3] = {xyb[0], xyb[1], xyb[2]};
+    long long cur_pitch = pitch;
+    int which = 0;
+    const dim3 blk(32, 8);
+    auto rows_range = [&](int margin, int &r0, int &r1) {
+        r0 = K.has_top ? -margin : 0;
+        r1 = rows + (K.has_bottom ? margin : 0);
+    };
+    if (K.gab || n_epf) {
+        CUDA_TRY(ctx, ctx->pp[0].ensure(sizeof(float) * 3 * plane));
+        CUDA_TRY(ctx, ctx->pp[1].ensure(sizeof(float) * 3 * plane));
+    }
+    auto pp_plane = [&](int w, int c) { return ctx->pp[w].as<float>() + (size_t)c * plane + (size_t)JXLB200_HALO_ROWS * W; };
+    if (K.gab) {
+        int r0, r1;
+        rows_range(reach[0], r0, r1);
+        const dim3 grid(ceil_div(W, 32), ceil_div(r1 - r0, 8));
+        k2_gab<<<grid, blk, 0, st>>>(K, cur[0], cur[1], cur[2], pp_plane(which, 0), pp_plane(which, 1), pp_plane(which, 2),
+                                     cur_pitch, pp_pitch, r0, r1);
+        ctx->launches++;
+        for (int c = 0; c < 3; c++) cur[c] = pp_plane(which, c);
+        cur_pitch = pp_pitch;
+        which ^= 1;
+    }
+    for (int i = 0; i < n_epf; i++) {
+        int r0, r1;
+        rows_range(reach[i + 1], r0, r1);
+        const dim3 grid(ceil_div(W, 32), ceil_div(r1 - r0, 8));
+        float *o0 = pp_plane(which, 0), *o1 = pp_plane(which, 1), *o2 = pp_plane(which, 2);
+        if (cur_pitch != pp_pitch) {
+            // EPF kernels use one pitch for input and output: bring the raw planes into a ping-pong set first
+            int c0, c1;
+            rows_range(reach[0], c0, c1);
+            for (int c = 0; c < 3; c++)
+                CUDA_TRY(ctx, cudaMemcpy2DAsync(pp_plane(which, c) + (long long)c0 * pp_pitch, sizeof(float) * pp_pitch,
+                                                cur[c] + (long long)c0 * cur_pitch, sizeof(float) * cur_pitch,
+                                                sizeof(float) * W, c1 - c0, cudaMemcpyDeviceToDevice, st));
+            for (int c = 0; c < 3; c++) cur[c] = pp_plane(which, c);
+            cur_pitch = pp_pitch;
+            which ^= 1;
+            o0 = pp_plane(which, 0); o1 = pp_plane(which, 1); o2 = pp_plane(which, 2);
+        }
+        switch (pass_id[i]) {
+        case 0: k2_epf<0><<<grid, blk, 0, st>>>(K, cur[0], cur[1], cur[2], o0, o1, o2, pp_pitch, inv_sigma, r0, r1); break;
+        case 1: k2_epf<1><<<grid, blk, 0, st>>>(K, cur[0], cur[1], cur[2], o0, o1, o2, pp_pitch, inv_sigma, r0, r1); break;
+        default: k2_epf<2><<<grid, blk, 0, st>>>(K, cur[0], cur[1], cur[2], o0, o1, o2, pp_pitch, inv_sigma, r0, r1); break;
+        }
+        ctx->launches++;
+        cur[0] = o0; cur[1] = o1; cur[2] = o2;
+        which ^= 1;
+    }
+    {
+        const dim3 grid(ceil_div(W, 32), ceil_div(rows, 8));
+        k2_color<<<grid, blk, 0, st>>>(K, cur[0], cur[1], cur[2], cur_pitch, out[0], out[1], out[2], (long long)W);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// device error flags -> status (dct_select out of range, sharpness outside 0..7)
+int check_flags(jxlb200_ctx *ctx) {
+    int rc = 0;
+    if (ctx->sched.p) {
+        int e = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&e, (char *)ctx->sched.p + offsetof(Sched, error), sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset((char *)ctx->sched.p + offsetof(Sched, error), 0, sizeof(int));
+            rc = ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select (HFMetadata.java:45-46)");
+        }
+    }
+    if (ctx->flags.p) {
+        int e = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&e, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset(ctx->flags.p, 0, sizeof(int) * 4);
+            rc = ctx->fail(JXLB200_E_STREAM, "Invalid EPF Sharpness (Frame.java:565-566)");
+        }
+    }
+    return rc;
+}
+
+struct HostMaps {   // device copies of the per-block maps, packed into one allocation
+    uint8_t *ds, *bo;
+    int32_t *hf, *sharp, *xfy, *bfy;
+};
+
+int upload_maps(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const uint8_t *ds, const uint8_t *bo, const int32_t *hf,
+                const int32_t *xfy, const int32_t *bfy, const int32_t *sharp, HostMaps &M) {
+    const size_t nb = (size_t)(p->width >> 3) * (p->height >> 3);
+    const size_t nt = (size_t)((p->width + 63) >> 6) * ((p->height + 63) >> 6);
+    const size_t nb4 = (nb + 3) & ~(size_t)3;
+    CUDA_TRY(ctx, ctx->in_maps.ensure(2 * nb4 + sizeof(int32_t) * (2 * nb + 2 * nt)));
+    char *base = (char *)ctx->in_maps.p;
+    M.ds = (uint8_t *)base; M.bo = (uint8_t *)(base + nb4);
+    M.hf = (int32_t *)(base + 2 * nb4); M.sharp = M.hf + nb; M.xfy = M.sharp + nb; M.bfy = M.xfy + nt;
+    cudaStream_t st = ctx->stream;
+    if (ds) CUDA_TRY(ctx, cudaMemcpyAsync(M.ds, ds, nb, cudaMemcpyHostToDevice, st));
+    if (bo) CUDA_TRY(ctx, cudaMemcpyAsync(M.bo, bo, nb, cudaMemcpyHostToDevice, st));
+    if (hf) CUDA_TRY(ctx, cudaMemcpyAsync(M.hf, hf, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    if (sharp) CUDA_TRY(ctx, cudaMemcpyAsync(M.sharp, sharp, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    if (xfy) CUDA_TRY(ctx, cudaMemcpyAsync(M.xfy, xfy, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
+    if (bfy) CUDA_TRY(ctx, cudaMemcpyAsync(M.bfy, bfy, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t jxlb200_create(int32_t device, jxlb200_ctx **out) {
+    if (!out) return JXLB200_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return JXLB200_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return JXLB200_E_CUDA;
+    jxlb200_ctx *ctx = new (std::nothrow) jxlb200_ctx();
+    if (!ctx) return JXLB200_E_CUDA;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return JXLB200_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    int rc = upload_constants(ctx);
+    if (rc) { fprintf(stderr, "jxlb200_create: %s\n", ctx->err.c_str()); jxlb200_destroy(ctx); return rc; }
+    *out = ctx;
+    return 0;
+}
+
+void jxlb200_destroy(jxlb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->lut8, &ctx->sigma, &ctx->flags,
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod};
+    for (DevBuf *b : all) b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *jxlb200_last_error(jxlb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int32_t jxlb200_set_stream(jxlb200_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return JXLB200_E_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int32_t jxlb200_sync(jxlb200_ctx *ctx) {
+    if (!ctx) return JXLB200_E_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_flags(ctx);
+}
+
+int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t jxlb200_qm_default_params(jxlb200_qm_params out[17]) {
+    if (!out) return JXLB200_E_ARG;
+    qm::default_params(out);
+    return 0;
+}
+
+int32_t jxlb200_qm_generate(const jxlb200_qm_params params[17], float *weights, int32_t offsets[51]) {
+    if (!params || !weights || !offsets) return JXLB200_E_ARG;
+    return qm::generate(params, weights, offsets);
+}
+
+int32_t jxlb200_set_qm_weights(jxlb200_ctx *ctx, const float *weights, const int32_t offsets[51]) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!weights || !offsets) return ctx->fail(JXLB200_E_ARG, "weights / offsets are NULL");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, ctx->wraw.ensure(sizeof(float) * JXLB200_QM_FLOATS));
+    CUDA_TRY(ctx, ctx->woff.ensure(sizeof(int) * 51));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wraw.p, weights, sizeof(float) * JXLB200_QM_FLOATS, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->woff.p, offsets, sizeof(int) * 51, cudaMemcpyHostToDevice, ctx->stream));
+    k0_expand_weights<<<dim3(16, 27), 256, 0, ctx->stream>>>(ctx->wraw.as<float>(), ctx->woff.as<int>(), ctx->tab, ctx->wexp.as<float>());
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host arrays may be freed by the caller after return
+    ctx->have_weights = true;
+    return 0;
+}
+
+int32_t jxlb200_vardct_invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, float *const xyb[3], int64_t xyb_pitch) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !xyb || xyb_pitch < p->width)
+        return ctx->fail(JXLB200_E_ARG, "NULL plane pointer or pitch < width");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, xyb, xyb_pitch);
+}
+
+int32_t jxlb200_restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_slab *slab,
+    const float *const xyb[3], int64_t xyb_pitch, const int32_t *hf_mul, const int32_t *sharpness, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!xyb || !out || xyb_pitch < p->width || (p->epf_iters > 0 && (!hf_mul || !sharpness)))
+        return ctx->fail(JXLB200_E_ARG, "NULL plane pointer or pitch < width");
+    for (int c = 0; c < 3; c++)
+        if (xyb[c] == out[c]) return ctx->fail(JXLB200_E_ARG, "in-place restore is not allowed");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return restore_dev(ctx, p, slab, xyb, xyb_pitch, hf_mul, sharpness, out);
+}
+
+int32_t jxlb200_vardct_reconstruct_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !out || (p->epf_iters > 0 && !sharpness))
+        return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t plane = (size_t)p->width * p->height;
+    CUDA_TRY(ctx, ctx->mid.ensure(sizeof(float) * 3 * plane));
+    float *mid[3] = {ctx->mid.as<float>(), ctx->mid.as<float>() + plane, ctx->mid.as<float>() + 2 * plane};
+    rc = invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, p->width);
+    if (rc) return rc;
+    return restore_dev(ctx, p, nullptr, mid, p->width, hf_mul, sharpness, out);
+}
+
+// host-buffer entry points ------------------------------------------------------------------------------------
+static int stage_in_planes(jxlb200_ctx *ctx, DevBuf &buf, const void *const src[3], size_t bytes_per_plane, void *dst[3]) {
+    CUDA_TRY(ctx, buf.ensure(3 * bytes_per_plane));
+    for (int c = 0; c < 3; c++) {
+        dst[c] = (char *)buf.p + c * bytes_per_plane;
+        if (!src[c]) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst[c], src[c], bytes_per_plane, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t bytes_per_plane, float *const out[3]) {
+    for (int c = 0; c < 3; c++) {
+        if (!out[c]) return ctx->fail(JXLB200_E_ARG, "NULL output plane pointer");
+        CUDA_TRY(ctx, cudaMemcpyAsync(out[c], dev[c], bytes_per_plane, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_flags(ctx);
+}
+
+int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !sharpness || !out)
+        return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)p->width * p->height, nb = npx / 64;
+    void *dq[3], *dlf[3];
+    if ((rc = stage_in_planes(ctx, ctx->in_q, (const void *const *)qcoeff, sizeof(int32_t) * npx, dq))) return rc;
+    if ((rc = stage_in_planes(ctx, ctx->in_lf, (const void *const *)lf, sizeof(float) * nb, dlf))) return rc;
+    HostMaps M;
+    if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
+    CUDA_TRY(ctx, ctx->out_planes.ensure(sizeof(float) * 3 * npx));
+    float *dout[3] = {ctx->out_planes.as<float>(), ctx->out_planes.as<float>() + npx, ctx->out_planes.as<float>() + 2 * npx};
+    rc = jxlb200_vardct_reconstruct_dev(ctx, p, (const int32_t *const *)dq, (const float *const *)dlf, M.ds, M.bo, M.hf, M.xfy, M.bfy,
+                                        M.sharp, dout);
+    if (rc) return rc;
+    return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
+}
+
+int32_t jxlb200_vardct_invert(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, float *const xyb[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !xyb)
+        return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)p->width * p->height, nb = npx / 64;
+    void *dq[3], *dlf[3];
+    if ((rc = stage_in_planes(ctx, ctx->in_q, (const void *const *)qcoeff, sizeof(int32_t) * npx, dq))) return rc;
+    if ((rc = stage_in_planes(ctx, ctx->in_lf, (const void *const *)lf, sizeof(float) * nb, dlf))) return rc;
+    HostMaps M;
+    if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, nullptr, M))) return rc;
+    CUDA_TRY(ctx, ctx->out_planes.ensure(sizeof(float) * 3 * npx));
+    float *dout[3] = {ctx->out_planes.as<float>(), ctx->out_planes.as<float>() + npx, ctx->out_planes.as<float>() + 2 * npx};
+    rc = invert_dev(ctx, p, (const int32_t *const *)dq, (const float *const *)dlf, M.ds, M.bo, M.hf, M.xfy, M.bfy, dout, p->width);
+    if (rc) return rc;
+    return stage_out_planes(ctx, dout, sizeof(float) * npx, xyb);
+}
+
+// one restoration stage on host planes: mode 0 Gaborish only, 1 EPF only, 2 colour only
+static int host_stage(jxlb200_ctx *ctx, const jxlb200_frame_params *p, int mode, const float *const in[3],
+                      const int32_t *hf_mul, const int32_t *sharp, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!in || !out) return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    jxlb200_frame_params q = *p;
+    q.gab = mode == 0 ? 1 : 0;
+    q.epf_iters = mode == 1 ? p->epf_iters : 0;
+    q.color_mode = mode == 2 ? p->color_mode : 0;
+    const size_t npx = (size_t)p->width * p->height;
+    void *din[3];
+    if ((rc = stage_in_planes(ctx, ctx->in_q, (const void *const *)in, sizeof(float) * npx, din))) return rc;
+    HostMaps M;
+    memset(&M, 0, sizeof(M));
+    if (mode == 1) {
+        if (!hf_mul || !sharp) return ctx->fail(JXLB200_E_ARG, "EPF needs hf_mul and sharpness");
+        if ((rc = upload_maps(ctx, p, nullptr, nullptr, hf_mul, nullptr, nullptr, sharp, M))) return rc;
+    }
+    CUDA_TRY(ctx, ctx->out_planes.ensure(sizeof(float) * 3 * npx));
+    float *dout[3] = {ctx->out_planes.as<float>(), ctx->out_planes.as<float>() + npx, ctx->out_planes.as<float>() + 2 * npx};
+    rc = restore_dev(ctx, &q, nullptr, (const float *const *)din, p->width, M.hf, M.sharp, dout);
+    if (rc) return rc;
+    return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
+}
+
+int32_t jxlb200_gaborish(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const float *const in[3], float *const out[3]) {
+    return host_stage(ctx, p, 0, in, nullptr, nullptr, out);
+}
+int32_t jxlb200_epf(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const float *const in[3], const int32_t *hf_mul,
+                    const int32_t *sharpness, float *const out[3]) {
+    return host_stage(ctx, p, 1, in, hf_mul, sharpness, out);
+}
+int32_t jxlb200_color_transform(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const float *const in[3], float *const out[3]) {
+    return host_stage(ctx, p, 2, in, nullptr, nullptr, out);
+}
+
+// ---- Modular ----
+int32_t jxlb200_modular_rct_dev(jxlb200_ctx *ctx, int32_t *const ch[3], int32_t h, int32_t w, int32_t rct_type) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!ch || !ch[0] || !ch[1] || !ch[2] || h < 0 || w < 0) return ctx->fail(JXLB200_E_ARG, "bad RCT arguments");
+    if (rct_type < 0 || rct_type >= 42) return ctx->fail(JXLB200_E_ARG, "rct_type outside 0..41");
+    if (h == 0 || w == 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const long long n = (long long)h * w;
+    const int grid = (int)min((long long)ctx->sms * 8, (n + 255) / 256);
+    k3_rct<<<grid, 256, 0, ctx->stream>>>(ch[0], ch[1], ch[2], n, rct_type % 7, rct_type / 7);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int32_t jxlb200_modular_squeeze_dev(jxlb200_ctx *ctx, const int32_t *avg, const int32_t *res, int32_t h_avg, int32_t w_avg,
+    int32_t h_res, int32_t w_res, int32_t horizontal, int32_t *out) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!avg || !out || h_avg < 0 || w_avg < 0 || h_res < 0 || w_res < 0) return ctx->fail(JXLB200_E_ARG, "bad squeeze arguments");
+    if (horizontal) {
+        if ((w_avg != w_res && w_avg != 1 + w_res) || h_res != h_avg) return ctx->fail(JXLB200_E_ARG, "Corrupted squeeze transform");
+    } else {
+        if ((h_avg != h_res && h_avg != 1 + h_res) || w_res != w_avg) return ctx->fail(JXLB200_E_ARG, "Corrupted squeeze transform");
+    }
+    if (h_avg == 0 || w_avg == 0) return 0;
+    if (!res && h_res > 0 && w_res > 0) return ctx->fail(JXLB200_E_ARG, "bad squeeze arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (horizontal) k5_squeeze_h<<<ceil_div(h_avg, 32), 32, 0, ctx->stream>>>(avg, res, h_avg, w_avg, w_res, out);
+    else k5_squeeze_v<<<ceil_div(w_avg, 128), 128, 0, ctx->stream>>>(avg, res, h_avg, h_res, w_avg, out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int32_t jxlb200_modular_palette_dev(jxlb200_ctx *ctx, const int32_t *idx, const int32_t *palette, int32_t h, int32_t w,
+    int32_t num_c, int32_t nb_colors, int32_t nb_deltas, int32_t d_pred, int32_t bit_depth, int32_t *const out[]) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!idx || !out || h < 0 || w < 0 || num_c < 1 || nb_colors < 0 || (nb_colors > 0 && !palette))
+        return ctx->fail(JXLB200_E_ARG, "bad palette arguments");
+    if (d_pred < 0 || d_pred > 13) return ctx->fail(JXLB200_E_ARG, "d_pred outside 0..13");
+    if (d_pred == 6) return ctx->fail(JXLB200_E_UNSUPPORTED, "palette delta with the weighted predictor (reference dereferences null pred[][])");
+    if (h == 0 || w == 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+    int *any = ctx->flags.as<int>() + 1;
+    PalArgs A{idx, palette, h, w, num_c, nb_colors, nb_deltas, d_pred, bit_depth};
+    const long long n = (long long)h * w;
+    const int grid = (int)min((long long)ctx->sms * 8, (n + 255) / 256);
+    CUDA_TRY(ctx, cudaMemsetAsync(any, 0, sizeof(int), ctx->stream));
+    for (int c = 0; c < num_c; c++) {
+        if (!out[c]) return ctx->fail(JXLB200_E_ARG, "NULL palette output channel");
+        k4_palette_gather<<<grid, 256, 0, ctx->stream>>>(A, c, out[c], any);
+        ctx->launches++;
+    }
+    if (d_pred != 0)   // predictor 0 adds 0 to every delta pixel
+        for (int c = 0; c < num_c; c++) {
+            k4_palette_delta<<<1, 1024, 0, ctx->stream>>>(A, out[c], any);
+            ctx->launches++;
+        }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+int32_t jxlb200_modular_rct(jxlb200_ctx *ctx, int32_t *const ch[3], int32_t h, int32_t w, int32_t rct_type) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!ch || !ch[0] || !ch[1] || !ch[2] || h < 0 || w < 0) return ctx->fail(JXLB200_E_ARG, "bad RCT arguments");
+    if (h == 0 || w == 0) return (rct_type < 0 || rct_type >= 42) ? ctx->fail(JXLB200_E_ARG, "rct_type outside 0..41") : 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(int32_t) * (size_t)h * w;
+    CUDA_TRY(ctx, ctx->mod.ensure(3 * bytes));
+    int32_t *d[3];
+    for (int c = 0; c < 3; c++) {
+        d[c] = (int32_t *)((char *)ctx->mod.p + c * bytes);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d[c], ch[c], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = jxlb200_modular_rct_dev(ctx, d, h, w, rct_type);
+    if (rc) return rc;
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(ch[c], d[c], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int32_t jxlb200_modular_squeeze(jxlb200_ctx *ctx, const int32_t *avg, const int32_t *res, int32_t h_avg, int32_t w_avg,
+    int32_t h_res, int32_t w_res, int32_t horizontal, int32_t *out) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!avg || !out || h_avg < 0 || w_avg < 0 || h_res < 0 || w_res < 0) return ctx->fail(JXLB200_E_ARG, "bad squeeze arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t na = (size_t)h_avg * w_avg, nr = (size_t)h_res * w_res, no = na + nr;
+    if (na == 0) return jxlb200_modular_squeeze_dev(ctx, avg, res, h_avg, w_avg, h_res, w_res, horizontal, out);
+    CUDA_TRY(ctx, ctx->mod.ensure(sizeof(int32_t) * (na + nr + no + 4)));
+    int32_t *da = ctx->mod.as<int32_t>(), *dr = da + na, *dout = dr + nr;
+    CUDA_TRY(ctx, cudaMemcpyAsync(da, avg, sizeof(int32_t) * na, cudaMemcpyHostToDevice, ctx->stream));
+    if (nr) CUDA_TRY(ctx, cudaMemcpyAsync(dr, res, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = jxlb200_modular_squeeze_dev(ctx, da, dr, h_avg, w_avg, h_res, w_res, horizontal, dout);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, sizeof(int32_t) * no, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int32_t jxlb200_modular_palette(jxlb200_ctx *ctx, const int32_t *idx, const int32_t *palette, int32_t h, int32_t w,
+    int32_t num_c, int32_t nb_colors, int32_t nb_deltas, int32_t d_pred, int32_t bit_depth, int32_t *const out[]) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!idx || !out || h < 0 || w < 0 || num_c < 1 || num_c > 4096 || nb_colors < 0 || (nb_colors > 0 && !palette))
+        return ctx->fail(JXLB200_E_ARG, "bad palette arguments");
+    if (h == 0 || w == 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w, np = (size_t)num_c * nb_colors;
+    CUDA_TRY(ctx, ctx->mod.ensure(sizeof(int32_t) * (n + np + (size_t)num_c * n + 4)));
+    int32_t *di = ctx->mod.as<int32_t>(), *dp = di + n, *dout = dp + np;
+    CUDA_TRY(ctx, cudaMemcpyAsync(di, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (np) CUDA_TRY(ctx, cudaMemcpyAsync(dp, palette, sizeof(int32_t) * np, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t **outs = (int32_t **)malloc(sizeof(int32_t *) * num_c);
+    for (int c = 0; c < num_c; c++) outs[c] = dout + (size_t)c * n;
+    int rc = jxlb200_modular_palette_dev(ctx, di, dp, h, w, num_c, nb_colors, nb_deltas, d_pred, bit_depth, outs);
+    if (!rc)
+        for (int c = 0; c < num_c && !rc; c++) {
+            if (!out[c]) { rc = ctx->fail(JXLB200_E_ARG, "NULL palette output channel"); break; }
+            cudaError_t e = cudaMemcpyAsync(out[c], outs[c], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync", e);
+        }
+    free(outs);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

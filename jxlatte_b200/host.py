@@ -1,0 +1,332 @@
+"""Host side of the drop-in boundary, above the C ABI (include/jxlb200.h).
+
+jxlatte is Java and this image has no JDK, so the Panama shim of INTEGRATION.md cannot be compiled here; this module
+makes the same downcalls through ctypes and mirrors the reference's method seams by name and argument meaning, so the
+parity tests read like tests of the reference itself (J/ = java/com/traneptora/jxlatte/ in the reference tree):
+
+    Reconstructor.generateWeights              HFGlobal.generateWeights             J/frame/vardct/HFGlobal.java:347-432
+    Reconstructor.invertVarDCT                 Frame.decodePassGroups tail          J/frame/Frame.java:361-374
+    Reconstructor.performGabConvolution        Frame.performGabConvolution          J/frame/Frame.java:505-542
+    Reconstructor.performEdgePreservingFilter  Frame.performEdgePreservingFilter    J/frame/Frame.java:544-636
+    Reconstructor.performColorTransforms       JXLCodestreamDecoder.performColorTransforms  J/JXLCodestreamDecoder.java:256-283
+    ModularTransforms.applyTransforms          ModularStream.applyTransforms        J/frame/modular/ModularStream.java:224-380
+
+Errors keep the reference's types: IllegalArgumentException -> ValueError, InvalidBitstreamException (an IOException)
+-> InvalidBitstreamError(IOError), UnsupportedOperationException -> NotImplementedError, CUDA failure -> IOError.
+Everything computes on the GPU; nothing here falls back to the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import QmParams, Slab  # noqa: F401
+from .params import FrameParams
+
+
+class InvalidBitstreamError(IOError):
+    """J/io/InvalidBitstreamException.java"""
+
+
+def _raise(rc, msg):
+    if rc == _lib.E_ARG:
+        raise ValueError(msg)
+    if rc == _lib.E_STREAM:
+        raise InvalidBitstreamError(msg)
+    if rc == _lib.E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise IOError(msg)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
+def qm_default_params():
+    """HFGlobal.getDefaultParams (J/frame/vardct/HFGlobal.java:79-188)."""
+    prm = (QmParams * 17)()
+    rc = _lib.lib().jxlb200_qm_default_params(prm)
+    if rc:
+        _raise(rc, "jxlb200_qm_default_params failed")
+    return prm
+
+
+def qm_generate(prm=None):
+    """HFGlobal.generateWeights for the 17 parameter sets -> (weights f32[3*131584], offsets i32[51]).  Host-side
+    table build, no GPU needed (the reference builds it once per frame in the HFGlobal constructor)."""
+    if prm is None:
+        prm = qm_default_params()
+    w = np.zeros(_lib.QM_FLOATS, np.float32)
+    off = np.zeros(51, np.int32)
+    rc = _lib.lib().jxlb200_qm_generate(prm, _ptr(w), _ptr(off))
+    if rc == _lib.E_STREAM:
+        raise InvalidBitstreamError("Negative or infinite weight")
+    if rc:
+        _raise(rc, "jxlb200_qm_generate failed")
+    return w, off
+
+
+class Reconstructor:
+    """One per decoder instance (JXLDecoder ctor / close(), J/JXLDecoder.java:17-46).  Not thread-safe, like the reference."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.jxlb200_create(int(device), C.byref(h))
+        if rc:
+            raise IOError("jxlb200_create(device=%d) failed with %d: no usable CUDA device (there is no CPU fallback)" % (device, rc))
+        self._h = h
+        self.device = device
+        self._weights = None
+
+    def close(self):
+        if self._h:
+            self._L.jxlb200_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing --
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, rc):
+        if rc:
+            _raise(rc, self._L.jxlb200_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.jxlb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(self._L.jxlb200_sync(self._h))
+
+    def launch_count(self):
+        return int(self._L.jxlb200_launch_count(self._h))
+
+    # -- HFGlobal --
+    def generateWeights(self, prm=None):
+        w, off = qm_generate(prm)
+        self.setWeights(w, off)
+        return w, off
+
+    def setWeights(self, weights, offsets):
+        w, off = _c(weights, np.float32), _c(offsets, np.int32)
+        if w.size != _lib.QM_FLOATS or off.size != 51:
+            raise ValueError("weights must hold 3*131584 floats and offsets 51 ints")
+        self._check(self._L.jxlb200_set_qm_weights(self._h, _ptr(w), _ptr(off)))
+        self._weights = (w, off)
+
+    # -- VarDCT --
+    def _state_args(self, st, H, W, with_sharp):
+        hb, wb, th, tw = H // 8, W // 8, (H + 63) // 64, (W + 63) // 64
+        q = [_c(st["qcoeff"][c], np.int32) for c in range(3)]
+        lf = [_c(st["lf"][c], np.float32) for c in range(3)]
+        ds, bo = _c(st["dct_select"], np.uint8), _c(st["block_origin"], np.uint8)
+        hm = _c(st["hf_mul"], np.int32)
+        xf, bf = _c(st["x_from_y"], np.int32), _c(st["b_from_y"], np.int32)
+        for a, shp, nm in ((q[0], (H, W), "qcoeff"), (lf[0], (hb, wb), "lf"), (ds, (hb, wb), "dct_select"),
+                           (bo, (hb, wb), "block_origin"), (hm, (hb, wb), "hf_mul"), (xf, (th, tw), "x_from_y"),
+                           (bf, (th, tw), "b_from_y")):
+            if a.shape != shp:
+                raise ValueError("%s has shape %s, expected %s" % (nm, a.shape, shp))
+        sh = None
+        if with_sharp:
+            sh = _c(st["sharpness"], np.int32)
+            if sh.shape != (hb, wb):
+                raise ValueError("sharpness has shape %s, expected %s" % (sh.shape, (hb, wb)))
+        return q, lf, ds, bo, hm, xf, bf, sh
+
+    def invertVarDCT(self, p, st):
+        """bakeDequantizedCoeffs + invertVarDCT for every pass group of the frame -> XYB planes f32[3,H,W]."""
+        H, W = p.height, p.width
+        q, lf, ds, bo, hm, xf, bf, _ = self._state_args(st, H, W, False)
+        out = np.empty((3, H, W), np.float32)
+        self._check(self._L.jxlb200_vardct_invert(
+            self._h, C.byref(p), _lib.planes([_ptr(a) for a in q]), _lib.planes([_ptr(a) for a in lf]),
+            _ptr(ds), _ptr(bo), _ptr(hm), _ptr(xf), _ptr(bf), _lib.planes([_ptr(out[c]) for c in range(3)])))
+        return out
+
+    def _stage(self, fn, p, planes_in, *extra):
+        inp = [_c(planes_in[c], np.float32) for c in range(3)]
+        if inp[0].shape != (p.height, p.width):
+            raise ValueError("planes have shape %s, expected %s" % (inp[0].shape, (p.height, p.width)))
+        out = np.empty((3, p.height, p.width), np.float32)
+        self._check(fn(self._h, C.byref(p), _lib.planes([_ptr(a) for a in inp]), *extra,
+                       _lib.planes([_ptr(out[c]) for c in range(3)])))
+        return out
+
+    def performGabConvolution(self, p, planes_in):
+        return self._stage(self._L.jxlb200_gaborish, p, planes_in)
+
+    def performEdgePreservingFilter(self, p, planes_in, hf_mul, sharpness):
+        hm, sh = _c(hf_mul, np.int32), _c(sharpness, np.int32)
+        shp = (p.height // 8, p.width // 8)
+        if hm.shape != shp or sh.shape != shp:
+            raise ValueError("hf_mul / sharpness must have shape %s" % (shp,))
+        return self._stage(self._L.jxlb200_epf, p, planes_in, _ptr(hm), _ptr(sh))
+
+    def performColorTransforms(self, p, planes_in):
+        return self._stage(self._L.jxlb200_color_transform, p, planes_in)
+
+    def reconstruct(self, p, st, out=None):
+        """The whole path on host buffers: invertVarDCT -> Gaborish -> EPF -> colour transform."""
+        H, W = p.height, p.width
+        q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True)
+        if out is None:
+            out = np.empty((3, H, W), np.float32)
+        self._check(self._L.jxlb200_vardct_reconstruct(
+            self._h, C.byref(p), _lib.planes([_ptr(a) for a in q]), _lib.planes([_ptr(a) for a in lf]),
+            _ptr(ds), _ptr(bo), _ptr(hm), _ptr(xf), _ptr(bf), _ptr(sh), _lib.planes([_ptr(out[c]) for c in range(3)])))
+        return out
+
+    # -- device-pointer calls (bench, multi-GPU): integers are CUdeviceptr values --
+    def reconstruct_dev(self, p, q, lf, ds, bo, hm, xf, bf, sh, out):
+        self._check(self._L.jxlb200_vardct_reconstruct_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf, sh,
+                                                           _lib.planes(out)))
+
+    def invert_dev(self, p, q, lf, ds, bo, hm, xf, bf, xyb, pitch):
+        self._check(self._L.jxlb200_vardct_invert_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf,
+                                                      _lib.planes(xyb), int(pitch)))
+
+    def restore_dev(self, p, slab, xyb, pitch, hm, sh, out):
+        self._check(self._L.jxlb200_restore_dev(self._h, C.byref(p), C.byref(slab) if slab is not None else None,
+                                                _lib.planes(xyb), int(pitch), hm, sh, _lib.planes(out)))
+
+    # -- Modular --
+    def inverseRCT(self, channels, rct_type):
+        """ModularStream.applyTransforms RCT branch: three equal-size channels, returns them as the reference leaves
+        channels[beginC .. beginC+2] (permutation applied)."""
+        v = [np.array(channels[c], dtype=np.int32, order="C", copy=True) for c in range(3)]
+        if not (v[0].shape == v[1].shape == v[2].shape):
+            raise InvalidBitstreamError("RCT must be performed on three equal size channels")
+        h, w = v[0].shape
+        self._check(self._L.jxlb200_modular_rct(self._h, _lib.planes([_ptr(a) for a in v]), h, w, int(rct_type)))
+        return v
+
+    def inversePalette(self, index_channel, palette, nb_deltas, d_pred, bit_depth):
+        """Palette branch: index channel [h,w] + palette [num_c, nb_colors] -> num_c channels."""
+        idx = _c(index_channel, np.int32)
+        pal = _c(palette, np.int32)
+        if pal.ndim != 2:
+            raise ValueError("palette must be [num_c, nb_colors]")
+        num_c, nb_colors = pal.shape
+        h, w = idx.shape
+        out = [np.zeros((h, w), np.int32) for _ in range(num_c)]
+        self._check(self._L.jxlb200_modular_palette(self._h, _ptr(idx), _ptr(pal) if pal.size else None, h, w, num_c, nb_colors,
+                                                    int(nb_deltas), int(d_pred), int(bit_depth),
+                                                    _lib.planes([_ptr(a) for a in out])))
+        return out
+
+    def inverseHorizontalSqueeze(self, orig, res):
+        return self._squeeze(orig, res, 1)
+
+    def inverseVerticalSqueeze(self, orig, res):
+        return self._squeeze(orig, res, 0)
+
+    def _squeeze(self, orig, res, horizontal):
+        a, r = _c(orig, np.int32), _c(res, np.int32)
+        ha, wa = a.shape
+        hr, wr = r.shape
+        out = np.zeros((ha, wa + wr) if horizontal else (ha + hr, wa), np.int32)
+        self._check(self._L.jxlb200_modular_squeeze(self._h, _ptr(a), _ptr(r) if r.size else None, ha, wa, hr, wr, horizontal, _ptr(out)))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ModularStream channel-list bookkeeping (host logic, J/frame/modular/ModularStream.java:66-185 and :224-380)
+# ---------------------------------------------------------------------------------------------------------------
+RCT, PALETTE, SQUEEZE = 0, 1, 2
+
+
+def default_squeeze_params(sizes, nb_meta):
+    """Default SqueezeParam list when the bitstream gives none (ModularStream.java:110-131).
+    sizes: [(h, w)] of the channel list at that point.  Returns [(horizontal, in_place, begin_c, num_c)]."""
+    first = nb_meta
+    count = len(sizes) - first
+    h, w = sizes[0]
+    out = []
+    if count > 2 and (h, w) == tuple(sizes[first + 1]):
+        out.append((True, False, first + 1, 2))
+        out.append((False, False, first + 1, 2))
+    if h >= w and h > 8:
+        out.append((False, True, first, count))
+        h = (h + 1) // 2
+    while w > 8 or h > 8:
+        if w > 8:
+            out.append((True, True, first, count))
+            w = (w + 1) // 2
+        if h > 8:
+            out.append((False, True, first, count))
+            h = (h + 1) // 2
+    return out
+
+
+def forward_channel_layout(sizes, squeeze_params):
+    """Replay of the constructor's squeeze bookkeeping (ModularStream.java:135-168): channel sizes after the forward
+    squeeze steps.  sizes: [(h, w)]; returns the new size list."""
+    ch = [tuple(s) for s in sizes]
+    for (horizontal, in_place, begin, num_c) in squeeze_params:
+        end = begin + num_c - 1
+        offset = end + 1 if in_place else len(ch)
+        for k in range(begin, end + 1):
+            h, w = ch[k]
+            if horizontal:
+                ch[k] = (h, (w + 1) // 2)
+                residu = (h, w // 2)
+            else:
+                ch[k] = ((h + 1) // 2, w)
+                residu = (h // 2, w)
+            ch.insert(offset + k - begin, residu)
+    return ch
+
+
+class ModularTransforms:
+    """ModularStream.applyTransforms over a decoded channel list, every transform running on the GPU.
+
+    transforms: list of dicts in bitstream order (they are undone in reverse, :228):
+        {"tr": RCT, "begin_c": b, "rct_type": t}
+        {"tr": PALETTE, "begin_c": b, "num_c": n, "nb_colors": k, "nb_deltas": d, "d_pred": p}
+        {"tr": SQUEEZE, "sp": [(horizontal, in_place, begin_c, num_c), ...]}   # explicit or default list
+    """
+
+    def __init__(self, reconstructor, bit_depth=8):
+        self.r = reconstructor
+        self.bit_depth = bit_depth
+
+    def applyTransforms(self, channels, transforms):
+        ch = [np.array(c, dtype=np.int32, order="C") for c in channels]
+        for tr in reversed(transforms):
+            if tr["tr"] == SQUEEZE:
+                for (horizontal, in_place, begin, num_c) in reversed(tr["sp"]):
+                    end = begin + num_c - 1
+                    offset = end + 1 if in_place else len(ch) + begin - end - 1
+                    for c in range(begin, end + 1):
+                        r = offset + c - begin
+                        ch[c] = (self.r.inverseHorizontalSqueeze if horizontal else self.r.inverseVerticalSqueeze)(ch[c], ch[r])
+                    del ch[offset:offset + end - begin + 1]
+            elif tr["tr"] == RCT:
+                b = tr["begin_c"]
+                ch[b:b + 3] = self.r.inverseRCT(ch[b:b + 3], tr["rct_type"])
+            elif tr["tr"] == PALETTE:
+                first = tr["begin_c"] + 1
+                outs = self.r.inversePalette(ch[first], ch[0][:tr["num_c"], :tr["nb_colors"]], tr["nb_deltas"], tr["d_pred"], self.bit_depth)
+                ch[first:first + 1] = outs
+                del ch[0]
+            else:
+                raise InvalidBitstreamError("Illegal Transform %r" % (tr["tr"],))
+        return ch

@@ -1,0 +1,165 @@
+"""Parity of the CUDA VarDCT path (through the C ABI) against the CPU oracle on identical synthetic frame state.
+
+Tolerances (BASELINE.json north_star): max abs error <= 1e-4 on linear float planes; <= 1 LSB after sRGB 8/16-bit
+quantisation.  Stage-1 XYB planes are held to 2e-5, the dequantised-coefficient arithmetic is bit-exact by construction.
+"""
+import numpy as np
+import pytest
+
+from jxlatte_b200 import synth, default_frame_params
+from jxlatte_b200.host import InvalidBitstreamError, qm_generate
+from jxlatte_b200.params import TRANSFORM_TYPES, TRANSFORM_NAMES
+
+pytestmark = pytest.mark.gpu
+
+TOL_LINEAR = 1e-4
+TOL_XYB = 2e-5
+
+
+def _state(w, h, seed, p, **kw):
+    qw, qo = qm_generate()
+    return synth.make_state(w, h, seed=seed, params=p, qm_weights=qw, qm_offsets=qo, **kw)
+
+
+def _single_type_state(t, p, seed):
+    """A frame tiled with one TransformType."""
+    H, W = p.height, p.width
+    st = _state(W, H, seed, p, mix="dct8")
+    _, _, ph, pw = TRANSFORM_TYPES[t]
+    bh, bw = ph // 8, pw // 8
+    hb, wb = H // 8, W // 8
+    assert hb % bh == 0 and wb % bw == 0
+    st["dct_select"][:] = t
+    org = np.zeros((hb, wb), np.uint8)
+    org[::bh, ::bw] = 1
+    st["block_origin"] = org
+    hm = st["hf_mul"][::bh, ::bw]
+    st["hf_mul"] = np.ascontiguousarray(np.repeat(np.repeat(hm, bh, axis=0), bw, axis=1))
+    rng = np.random.default_rng(seed + 99)
+    # denser, small coefficients so every basis function is exercised
+    q = (rng.integers(-3, 4, size=(3, H, W)) * (rng.random((3, H, W)) < 0.2)).astype(np.int32)
+    st["qcoeff"] = q
+    return st
+
+
+@pytest.mark.parametrize("t", range(27))
+def test_invert_every_transform_type(recon, orc, t):
+    _, _, ph, pw = TRANSFORM_TYPES[t]
+    H, W = max(256, ph), max(256, pw)
+    p = default_frame_params(W, H, global_scale=32768)
+    st = _single_type_state(t, p, seed=100 + t)
+    ref = orc.vardct_invert(p, st, nthreads=8)
+    got = recon.invertVarDCT(p, st)
+    err = np.abs(got - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    assert err <= TOL_XYB * scale, "%s: max abs err %g (range %g)" % (TRANSFORM_NAMES[t], err, scale)
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+@pytest.mark.parametrize("shape", [(512, 512), (1280, 720), (264, 8), (8, 264), (776, 520)])
+def test_invert_mixed_partition(recon, orc, shape, aligned):
+    W, H = shape
+    p = default_frame_params(W, H)
+    st = _state(W, H, 7 + W + H, p, aligned=aligned)
+    ref = orc.vardct_invert(p, st, nthreads=8)
+    got = recon.invertVarDCT(p, st)
+    assert np.abs(got - ref).max() <= TOL_XYB * max(1.0, np.abs(ref).max())
+
+
+def test_gaborish(recon, orc):
+    p = default_frame_params(328, 200)
+    rng = np.random.default_rng(3)
+    planes = rng.random((3, 200, 328), dtype=np.float32)
+    ref = orc.gab(p, planes)
+    got = recon.performGabConvolution(p, planes)
+    assert np.abs(got - ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("iters", [1, 2, 3])
+def test_epf(recon, orc, iters):
+    W, H = 328, 200
+    p = default_frame_params(W, H, epf_iters=iters)
+    rng = np.random.default_rng(4 + iters)
+    planes = (rng.random((3, H, W), dtype=np.float32) * np.array([0.05, 1.0, 1.0], np.float32)[:, None, None])
+    planes = planes * 0.2 + 0.4
+    hm = rng.integers(1, 5, size=(H // 8, W // 8)).astype(np.int32)
+    sh = rng.integers(0, 8, size=(H // 8, W // 8)).astype(np.int32)   # includes 0 = pass-through blocks
+    ref = orc.epf(p, planes, hm, sh, nthreads=8)
+    got = recon.performEdgePreservingFilter(p, planes, hm, sh)
+    assert np.abs(got - ref).max() <= 5e-6
+
+
+def test_epf_rejects_bad_sharpness(recon):
+    p = default_frame_params(64, 64, epf_iters=1)
+    planes = np.zeros((3, 64, 64), np.float32)
+    hm = np.ones((8, 8), np.int32)
+    sh = np.full((8, 8), 9, np.int32)
+    with pytest.raises(InvalidBitstreamError):
+        recon.performEdgePreservingFilter(p, planes, hm, sh)
+
+
+def test_color_transforms(recon, orc):
+    W, H = 256, 64
+    rng = np.random.default_rng(5)
+    planes = rng.random((3, H, W), dtype=np.float32)
+    planes[0] = (planes[0] - 0.5) * 0.05
+    for mode in (0, 1, 2, 3):
+        p = default_frame_params(W, H, color_mode=mode)
+        ref = orc.color(p, planes)
+        got = recon.performColorTransforms(p, planes)
+        assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), mode
+
+
+def _srgb_quantise(lin, bits):
+    """TransferFunction.TF_SRGB.fromLinearF (J/color/TransferFunction.java:39-43) + ImageBuffer.castToIntWithMax (:129-145)."""
+    lin = lin.astype(np.float32)
+    a = np.where(lin <= np.float32(0.0031308), lin * np.float32(12.92),
+                 np.float32(1.055) * np.power(np.maximum(lin, 0), np.float32(1.0 / 2.4), dtype=np.float32) - np.float32(0.055))
+    mx = (1 << bits) - 1
+    v = (a.astype(np.float32) * np.float32(mx) + np.float32(0.5)).astype(np.int64)
+    return np.clip(v, 0, mx)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(512, 512), iters=1, gab=True),      # lenna-like: gab on, EPF 1
+    dict(shape=(1280, 720), iters=1, gab=True),     # bbb-like
+    dict(shape=(1024, 768), iters=3, gab=True),     # 8K-config settings at a size the oracle does in seconds
+    dict(shape=(520, 264), iters=2, gab=False),
+    dict(shape=(264, 520), iters=0, gab=True),
+    dict(shape=(256, 256), iters=0, gab=False),
+])
+def test_full_reconstruction(recon, orc, cfg):
+    W, H = cfg["shape"]
+    p = default_frame_params(W, H, epf_iters=cfg["iters"], gab=cfg["gab"])
+    st = _state(W, H, 11 + W, p)
+    ref = orc.vardct_reconstruct(p, st, nthreads=8)
+    got = recon.reconstruct(p, st)
+    err = np.abs(got - ref).max()
+    assert err <= TOL_LINEAR, "max abs err %g on linear planes" % err
+    for bits in (8, 16):
+        d = np.abs(_srgb_quantise(got, bits) - _srgb_quantise(ref, bits)).max()
+        assert d <= 1, "%d-bit sRGB differs by %d LSB" % (bits, d)
+
+
+def test_invalid_transform_type_is_reported(recon):
+    p = default_frame_params(64, 64)
+    st = _state(64, 64, 1, p, mix="dct8")
+    st["dct_select"][3, 3] = 31
+    with pytest.raises(InvalidBitstreamError):
+        recon.invertVarDCT(p, st)
+
+
+def test_chroma_subsampling_is_unsupported(recon):
+    p = default_frame_params(64, 64)
+    p.shift_x[0] = 1
+    st = _state(64, 64, 1, default_frame_params(64, 64), mix="dct8")
+    with pytest.raises(NotImplementedError):
+        recon.invertVarDCT(p, st)
+
+
+def test_bad_arguments(recon):
+    p = default_frame_params(64, 64)
+    st = _state(64, 64, 1, p, mix="dct8")
+    st["lf"] = st["lf"][:, :4]
+    with pytest.raises(ValueError):
+        recon.invertVarDCT(p, st)

@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- reconstructed MP/s of the VarDCT reconstruction path (dequant -> IDCT -> CfL/LLF -> Gaborish -> EPF ->
+XYB->linear) on B200, with the roofline of the dominant kernel and the CPU restatement timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 8k|batch2048|split16k]
+
+A "step" = one pass of the hot path over one batch of synthetic post-entropy frame state.
+  8k        (default) one 7680x4320 frame per GPU, mixed varblocks DCT8..DCT256+AFV, gab on, EPF 3 iterations; N GPUs
+            = a batch of N frames sharded per image, no communication (weak scaling)
+  batch2048 eight 2048x2048 frames per GPU per step, EPF 1 iteration (per-image sharding, weak scaling)
+  split16k  one 16384x16384 frame split by group rows over the N GPUs, 7 halo rows exchanged with NCCL (strong scaling)
+Prints ONE JSON line on rank 0.  Under torchrun one process per GPU; barrier + synchronize around the timed region,
+device time by CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PX = 24.35      # 12 coeff + 12 out + 0.1875 LF + 0.1563 maps + ~0.002
+BYTES_PER_PX_K2 = 24.13   # stage 2 alone: XYB in, linear out, sigma maps
+METRIC = "reconstructed MP/s (VarDCT dequant->XYB)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([s.strip() for s in o])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(W, H, seed, epf_iters):
+    from jxlatte_b200 import synth, default_frame_params
+    from jxlatte_b200.host import qm_generate
+    p = default_frame_params(W, H, epf_iters=epf_iters, gab=True)
+    qw, qo = qm_generate()
+    st = synth.make_state(W, H, seed=seed, params=p, qm_weights=qw, qm_offsets=qo)
+    return p, st, qw, qo
+
+
+def cpu_baseline(nthreads, sample=(2048, 2048), epf_iters=3, reps=1):
+    """The CPU restatement of jxlatte's algorithm (oracle 'port'; not the JVM) on a bounded sample of the workload."""
+    from oracle import oracle
+    W, H = sample
+    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 77, epf_iters)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.vardct_reconstruct(p, st, nthreads=nthreads)
+    dt = (time.perf_counter() - t0) / reps
+    return W * H / 1e6 / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  jxlatte is pure Java and no JVM exists in
+    this image, so this arm times the C restatement (oracle/, kind 'port') on all host cores, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    iters = 3 if args.workload != "batch2048" else 1
+    W, H = 1024, 1024
+    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 78, iters)
+    for _ in range(min(args.warmup, 2)):
+        oracle.vardct_reconstruct(p, st, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.vardct_reconstruct(p, st, nthreads=cores)
+    dt = time.perf_counter() - t0
+    v = W * H * args.steps / 1e6 / dt
+    sample = "%dx%d sample of the workload per step, same varblock mix / gab / EPF %d iters" % (W, H, iters)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, iters),
+            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, iters):
+    names = {"8k": "synthetic 7680x4320 VarDCT frame per GPU (batch of N frames sharded per image), mixed varblocks DCT8-DCT256+AFV, gab on, EPF 3 iterations",
+             "batch2048": "8 synthetic 2048x2048 VarDCT frames per GPU per step (per-image sharding), mixed varblocks, gab on, EPF 1 iteration",
+             "split16k": "synthetic 16384x16384 VarDCT frame split by group rows over N GPUs, NCCL halo rows, mixed varblocks, gab on, EPF 3 iterations"}
+    return {"workload": names[args.workload], "epf_iters": iters, "parallelism": "per-image shard x%d" % args.gpus if args.workload != "split16k" else "group-row split x%d" % args.gpus,
+            "l2": "inputs per step exceed the 126 MB L2 (no flush needed)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from jxlatte_b200.host import Reconstructor, Slab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    iters = 1 if args.workload == "batch2048" else 3
+    if args.workload == "8k":
+        W, H, nframes = 7680, 4320, 1
+    elif args.workload == "batch2048":
+        W, H, nframes = 2048, 2048, 8
+    else:
+        W, H, nframes = 16384, 16384, 1
+
+    rec = Reconstructor(local)
+    # a real (non-legacy) stream shared by torch's events and the library's kernels: a NULL handle would mean
+    # "the context's own stream" to jxlb200_set_stream and the events would time nothing
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    rec.set_stream(stream.cuda_stream)
+
+    slab = None
+    if args.workload == "split16k":
+        # contiguous group rows per rank; every rank builds the same frame (same seed) and keeps its own rows
+        from jxlatte_b200.multigpu import slab_rows
+        y0, rows = slab_rows(H, world, rank)
+        full_h = H
+    p, st, qw, qo = make_inputs(W, H if args.workload != "split16k" else rows, 0x4A584C00 + 2 + rank, iters)
+    rec.setWeights(qw, qo)
+
+    def dev_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    frames = []
+    for f in range(nframes):
+        if f > 0:
+            _, stf, _, _ = make_inputs(W, H, 0x4A584C00 + 100 * f + rank, iters)
+        else:
+            stf = st
+        d = {k: dev_t(stf[k]) for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
+        d["out"] = torch.empty((3, stf["height"], W), dtype=torch.float32, device=dev)
+        frames.append(d)
+
+    halo = None
+    if args.workload == "split16k":
+        from jxlatte_b200.multigpu import SplitFrame
+        halo = SplitFrame(rec, p, frames[0], y0, rows, full_h, rank, world, dev)
+
+    def step():
+        if halo is not None:
+            halo.step()
+            return
+        for d in frames:
+            rec.reconstruct_dev(p, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
+                                d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
+                                d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
+                                [d["out"][c].data_ptr() for c in range(3)])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    rec.sync()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = rec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rec.launch_count() - l0
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+    rec.sync()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    px_per_step_all = (W * H * nframes * world) if args.workload != "split16k" else W * H
+    value = px_per_step_all * args.steps / 1e6 / (ms_max / 1e3)
+
+    # ---- stage timing for the roofline of the dominant kernel (rank 0, same process, CUDA events on the same stream) ----
+    roof = None
+    e2e = None
+    cpu = None
+    if rank == 0 and halo is None:
+        d = frames[0]
+        plane = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        q = [d["qcoeff"][c].data_ptr() for c in range(3)]
+        lf = [d["lf"][c].data_ptr() for c in range(3)]
+        xyb = [plane[c].data_ptr() for c in range(3)]
+        out = [d["out"][c].data_ptr() for c in range(3)]
+
+        def timed(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(n):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        t1 = timed(lambda: rec.invert_dev(p, q, lf, d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
+                                          d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), xyb, W))
+        t2 = timed(lambda: rec.restore_dev(p, None, xyb, W, d["hf_mul"].data_ptr(), d["sharpness"].data_ptr(), out))
+        peak, which = peaks()
+        dom = "stage 2 (Gaborish+EPF+colour)" if t2 >= t1 else "stage 1 (dequant+CfL+LLF+IDCT)"
+        bpp = BYTES_PER_PX_K2 if t2 >= t1 else BYTES_PER_PX
+        ach = bpp * W * H / (max(t1, t2) / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": dom, "peak_source": which, "algorithmic_bytes_per_px": bpp,
+                "stage_ms": {"stage1_dequant_idct": t1, "stage2_gab_epf_color": t2},
+                "pipeline_frac": BYTES_PER_PX * W * H / ((t1 + t2) / 1e3) / 1e9 / peak}
+
+        # ---- e2e: the host-buffer C-ABI call a reference-side shim makes; pinned host memory, H2D + D2H inside ----
+        hst = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in
+               ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
+        hout = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+        hnp = {k: v.numpy() for k, v in hst.items()}
+        houtn = hout.numpy()
+        rec.set_stream(None)
+        for _ in range(2):
+            rec.reconstruct(p, hnp, out=houtn)
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rec.reconstruct(p, hnp, out=houtn)
+        dt = (time.perf_counter() - t0) / n_e2e
+        h2d = sum(int(v.numel() * v.element_size()) for v in hst.values())
+        e2e = {"value": W * H / 1e6 / dt, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(hout.numel() * 4),
+               "ms_per_step": dt * 1e3, "api": "jxlb200_vardct_reconstruct (host buffers, pinned)"}
+        rec.set_stream(stream.cuda_stream)
+
+        if world == 1:
+            cores = os.cpu_count() or 1
+            v, dt_cpu = cpu_baseline(cores, sample=(2048, 2048), epf_iters=iters)
+            cpu = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+                   "sample": "one 2048x2048 frame of the same synthetic workload (%.1f s), C restatement of jxlatte's algorithm, not the JVM" % dt_cpu}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.workload == "split16k" else "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, iters), "gpu_launches": int(launches),
+                "clocks": sampler.summary() if sampler else None}
+        if roof:
+            line["roofline"] = roof
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    rec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="8k", choices=["8k", "batch2048", "split16k"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

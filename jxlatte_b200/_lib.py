@@ -14,6 +14,8 @@ SO_PATH = os.path.join(_HERE, "libjxlb200.so")
 OK, E_ARG, E_STREAM, E_UNSUPPORTED, E_CUDA = 0, -1, -2, -3, -4
 QM_FLOATS = 3 * 131584
 HALO_ROWS = 8
+OPT_STAGE2 = 1
+STAGE2_AUTO, STAGE2_STAGED, STAGE2_FUSED = 0, 1, 2
 
 
 class QmParams(C.Structure):
@@ -42,6 +44,7 @@ SYMBOLS = {
     "jxlb200_set_stream": (_i32, [_vp, _vp]),
     "jxlb200_sync": (_i32, [_vp]),
     "jxlb200_launch_count": (C.c_int64, [_vp]),
+    "jxlb200_set_option": (_i32, [_vp, _i32, _i32]),
     "jxlb200_qm_default_params": (_i32, [C.POINTER(QmParams)]),
     "jxlb200_qm_generate": (_i32, [C.POINTER(QmParams), _vp, _vp]),
     "jxlb200_set_qm_weights": (_i32, [_vp, _vp, _vp]),

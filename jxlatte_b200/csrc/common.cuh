@@ -50,6 +50,7 @@ struct K1Params {
     const int32_t *xfy, *bfy;
     const int32_t *cfl_gate;    // per 64x64 tile: raster index of the varblock origin covering the tile's corner cell
     const float *wexp;          // QM weights re-laid-out per TransformType in storage orientation
+    const float *cos_big;       // MathHelper.cosineLut levels 6..8 (lengths 64, 128, 256), [n-1][k]
     int W, H, wb, hb, tw;
     float sf[3];                // scaleFactor[c]  (HFCoefficients.java:270-275)
     float qb[3];                // quantBias

@@ -38,8 +38,9 @@ struct jxlb200_ctx {
     std::string err;
     int64_t launches = 0;
     bool have_weights = false;
+    int opt_stage2 = 0;
 
-    DevBuf sched, items, gate, wraw, woff, wexp, lut8, sigma, flags;
+    DevBuf sched, items, gate, wraw, woff, wexp, cosbig, lut8, sigma, flags;
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
@@ -68,7 +69,7 @@ const float kScaleF[32] = {
 };
 
 template <int N, int PASS> cudaError_t big_attr() {
-    return cudaFuncSetAttribute(k1_big<N, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigSmem<N>::kBytes);
+    return cudaFuncSetAttribute(k1_big<N, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigSmem<N, PASS>::kBytes);
 }
 
 int upload_constants(jxlb200_ctx *ctx) {
@@ -78,9 +79,6 @@ int upload_constants(jxlb200_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_big_types, h_big_types, sizeof(h_big_types)));
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_afv, kAfvBasis, sizeof(kAfvBasis)));
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_llf_scale, kScaleF, sizeof(kScaleF)));
-    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec64, h_sec64, sizeof(h_sec64)));
-    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec128, h_sec128, sizeof(h_sec128)));
-    CUDA_TRY(ctx, cudaMemcpyToSymbol(c_sec256, h_sec256, sizeof(h_sec256)));
     // MathHelper.cosineLut (J/util/MathHelper.java:19-30): (float)(sqrt2 * cos(pi (n+1) (k+0.5) / s)), double math
     float cosv[1302];
     int offs[6] = {0, 0, 0, 0, 0, 0}, o = 0;
@@ -93,6 +91,28 @@ int upload_constants(jxlb200_ctx *ctx) {
     }
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_cos, cosv, sizeof(float) * o));
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_cos_off, offs, sizeof(offs)));
+    // levels 6..8 (lengths 64, 128, 256) live in global memory; the kernels rely on the table's exact symmetry
+    // lut[n-1][s-1-k] == (-1)^n lut[n-1][k] in float, so verify it here rather than assume it
+    {
+        float *big = (float *)malloc(sizeof(float) * COS_BIG_FLOATS);
+        bool symmetric = true;
+        for (int l = 1; l <= 8; l++) {
+            const int s = 1 << l;
+            float *dst = l >= 6 ? big + cos_big_off(s) : nullptr;
+            for (int n = 0; n < s - 1; n++)
+                for (int k = 0; k < s; k++) {
+                    const float a = (float)(root2 * cos(M_PI * (n + 1) * (k + 0.5) / s));
+                    const float b = (float)(root2 * cos(M_PI * (n + 1) * ((s - 1 - k) + 0.5) / s));
+                    if (a != (((n + 1) & 1) ? -b : b)) symmetric = false;
+                    if (dst) dst[n * s + k] = a;
+                }
+        }
+        if (!symmetric) { free(big); return ctx->fail(JXLB200_E_CUDA, "cosine table is not exactly symmetric on this host libm"); }
+        cudaError_t e = ctx->cosbig.ensure(sizeof(float) * COS_BIG_FLOATS);
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->cosbig.p, big, sizeof(float) * COS_BIG_FLOATS, cudaMemcpyHostToDevice);
+        free(big);
+        if (e != cudaSuccess) return ctx->fail(JXLB200_E_CUDA, "cosine table upload", e);
+    }
     int wo = 0;
     for (int t = 0; t < 27; t++) { ctx->tab.wexp_off[t] = wo; wo += 3 * h_tt[t].bh * h_tt[t].bw * 64; }
     CUDA_TRY(ctx, cudaMemcpyToSymbol(c_tab, &ctx->tab, sizeof(DevTables)));
@@ -119,8 +139,8 @@ int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
 }
 
 template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls) {
-    const int per_sm = N >= 128 ? 1 : (N == 64 ? 2 : 4);
-    k1_big<N, PASS><<<ctx->sms * per_sm, 384, BigSmem<N>::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
+    const int per_sm = max(1, min(4, (227 * 1024) / (BigSmem<N, PASS>::kBytes + 1024)));
+    k1_big<N, PASS><<<ctx->sms * per_sm, BIG_THREADS, BigSmem<N, PASS>::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
     ctx->launches++;
 }
 
@@ -140,9 +160,9 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     const int g0 = min(ctx->sms * 4, ceil_div(ncells, 256));
     k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, S);
     k0_plan<<<1, 32, 0, st>>>(S);
-    k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>());
-    k0_cfl_gate<<<ceil_div(tw * th, 128), 128, 0, st>>>(ds, bo, hb, wb, th, tw, ctx->gate.as<int>());
-    ctx->launches += 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->gate.p, 0x7f, sizeof(int) * (size_t)tw * th, st));
+    k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>(), ctx->gate.as<int>(), tw);
+    ctx->launches += 3;
 
     K1Params P;
     for (int c = 0; c < 3; c++) { P.q[c] = q[c]; P.lf[c] = lf[c]; P.out[c] = out[c]; }
@@ -150,6 +170,7 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     P.dct_select = ds; P.hf_mul = hf_mul; P.xfy = xfy; P.bfy = bfy;
     P.cfl_gate = ctx->gate.as<int>();
     P.wexp = ctx->wexp.as<float>();
+    P.cos_big = ctx->cosbig.as<float>();
     P.W = W; P.H = H; P.wb = wb; P.hb = hb; P.tw = tw;
     // HFCoefficients.dequantizeHFCoefficients :270-275
     const float gs = 65536.0f / p->global_scale;
@@ -223,12 +244,13 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                      ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-    if (k2_fused_supported(K)) {
+    if (ctx->opt_stage2 != 1 && k2_fused_supported(K)) {
         int rc = k2_fused_launch(ctx, K, inv_sigma);
         if (rc) return rc;
         CUDA_TRY(ctx, cudaGetLastError());
         return 0;
     }
+    if (ctx->opt_stage2 == 2) return ctx->fail(JXLB200_E_UNSUPPORTED, "fused stage 2 does not take this frame");
 
     // ---- staged fallback-free path: one kernel per stage, planes ping-pong through ctx->pp ----
     const long long pp_pitch = W;
@@ -378,7 +400,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->lut8, &ctx->sigma, &ctx->flags,
+    DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
                      &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod};
     for (DevBuf *b : all) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -400,6 +422,12 @@ int32_t jxlb200_sync(jxlb200_ctx *ctx) {
 }
 
 int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 2) { ctx->opt_stage2 = value; return 0; }
+    return ctx->fail(JXLB200_E_ARG, "unknown option or value");
+}
 
 int32_t jxlb200_qm_default_params(jxlb200_qm_params out[17]) {
     if (!out) return JXLB200_E_ARG;

@@ -65,8 +65,10 @@ __global__ void k0_plan(Sched *s) {
 }
 
 // items[start[t] + i] = (by << 16) | bx of the i-th varblock of type t (order within a type is arbitrary)
+// Also fills the CfL gate: gate[tile] = raster index (by * wb + bx) of the origin of the varblock that covers the tile's
+// top-left cell (tiles are 8x8 cells); the gate array is preset to 0x7f7f7f7f ("never visited").
 __global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int hb, int wb, Sched *s,
-                           int *__restrict__ items) {
+                           int *__restrict__ items, int *__restrict__ gate, int tw) {
     __shared__ int h[27];
     __shared__ int base[27];
     if (threadIdx.x < 27) h[threadIdx.x] = 0;
@@ -87,28 +89,13 @@ __global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__rest
         const int t = ds[i];
         if (bo[i] && t <= 26) {
             const int slot = s->start[t] + base[t] + atomicAdd(&h[t], 1);
-            items[slot] = ((i / wb) << 16) | (i % wb);
+            const int by = i / wb, bx = i % wb;
+            items[slot] = (by << 16) | bx;
+            const TTInfo tt = c_tt[t];
+            for (int cy = (by + 7) & ~7; cy < by + tt.bh; cy += 8)
+                for (int cx = (bx + 7) & ~7; cx < bx + tt.bw; cx += 8) gate[(cy >> 3) * tw + (cx >> 3)] = i;
         }
     }
-}
-
-// gate[tile] = raster index (by * wb + bx) of the origin of the varblock that covers the tile's top-left cell
-__global__ void k0_cfl_gate(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int hb, int wb, int th, int tw,
-                            int *__restrict__ gate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= th * tw) return;
-    const int cy = (i / tw) * 8, cx = (i % tw) * 8;   // corner cell
-    const int t = ds[cy * wb + cx];
-    int found = 0x7fffffff;                           // "never visited" if the map is inconsistent
-    if (t <= 26) {
-        const TTInfo tt = c_tt[t];
-        for (int dy = 0; dy < tt.bh && dy <= cy; dy++)
-            for (int dx = 0; dx < tt.bw && dx <= cx; dx++) {
-                const int o = (cy - dy) * wb + (cx - dx);
-                if (bo[o] && ds[o] == t) { found = o; dy = 64; break; }
-            }
-    }
-    gate[i] = found;
 }
 
 // QM weights (HFGlobal.weights: [parameterIndex][c][matrixH][matrixW]) -> per TransformType, storage orientation

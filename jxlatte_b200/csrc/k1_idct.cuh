@@ -9,13 +9,11 @@
 // Three kernel families, each persistent over the K0 work lists:
 //   k1_small   8x8-class (DCT8, Hornuss, DCT2, DCT4, DCT4x8, DCT8x4, AFV0-3): one thread per varblock-channel, 64
 //              coefficients in registers, staged through shared memory so global traffic stays row-coalesced.
-//   k1_medium  16/32-class (8 shapes): tile in shared memory, one thread per line, Lee IDCT in registers.
-//   k1_big     any side >= 64: two passes (columns, then rows) over 32-line strips; lines longer than 32 are split
-//              around the 32-point register kernel (LeeGather / lee_combine); the intermediate lives in the output
-//              plane (L2-resident between the passes).
-// Dequantisation and CfL use explicit round-to-nearest mul/add/div so the dequantised coefficients are bit-identical
-// to the Java float arithmetic (which never contracts to FMA); the transforms themselves are O(N log N) instead of
-// the reference's O(N^2) sums and agree to float rounding.
+//   k1_medium  16/32-class (8 shapes): tile in shared memory, one thread per line, IDCT in registers.
+//   k1_big     any side >= 64: two passes (columns, then rows) over 32-line strips, lane = line, each warp owning 32
+//              outputs of 32 lines; the intermediate lives in the output plane (L2-resident between the passes).
+// Every float operation is an explicit round-to-nearest mul/add/sub/div in the Java's order (Java never contracts to
+// FMA), so the XYB planes this stage writes are bit-identical to the reference's (see transforms.cuh for why).
 #pragma once
 #include "common.cuh"
 #include "k0_lists.cuh"
@@ -25,13 +23,10 @@ __constant__ float c_afv[256];        // PassGroup.AFV_BASIS (J/frame/group/Pass
 __constant__ float c_cos[1302];       // MathHelper.cosineLut levels 1..5 (lengths 2..32), [n][k], J/util/MathHelper.java:17-30
 __constant__ int c_cos_off[6];        // offset of level l
 __constant__ float c_llf_scale[32];   // LLFScale.SCALE_F (J/frame/vardct/LLFScale.java:7-23)
-__constant__ float c_sec64[32], c_sec128[64], c_sec256[128];
 __constant__ DevTables c_tab;
 
-struct SecDev {
-    __device__ __forceinline__ float operator()(int n, int k) const {
-        return n == 64 ? c_sec64[k] : n == 128 ? c_sec128[k] : c_sec256[k];
-    }
+struct CosLut {   // packed MathHelper.cosineLut, constant-bank operand once the index is a compile-time constant
+    __device__ __forceinline__ float operator()(int i) const { return c_cos[i]; }
 };
 
 __device__ __forceinline__ int ilog2_pow2(int v) { return 31 - __clz(v); }
@@ -179,13 +174,13 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
             for (int e = 0; e < 64; e++) v[e] = tile[e * SMALL_PITCH + tid];
             SmemOut out{tile + tid};
             switch (type) {
-            case 0: inv_dct8x8(v, out); break;
+            case 0: inv_dct8x8(v, CosLut(), out); break;
             case 1: inv_hornuss(v, out); break;
             case 2: inv_dct2(v, out); break;
-            case 3: inv_dct4(v, out); break;
-            case 12: inv_dct4x8<false>(v, out); break;
-            case 13: inv_dct4x8<true>(v, out); break;
-            default: inv_afv(v, (type == 16 || type == 17) ? 1 : 0, (type == 15 || type == 17) ? 1 : 0, AfvBasis(), out); break;
+            case 3: inv_dct4(v, CosLut(), out); break;
+            case 12: inv_dct4x8<false>(v, CosLut(), out); break;
+            case 13: inv_dct4x8<true>(v, CosLut(), out); break;
+            default: inv_afv(v, (type == 16 || type == 17) ? 1 : 0, (type == 15 || type == 17) ? 1 : 0, AfvBasis(), CosLut(), out); break;
             }
         }
         __syncthreads();
@@ -213,7 +208,7 @@ template <int N> __device__ __forceinline__ void line_idct(float *p, int stride)
     float v[N];
 #pragma unroll
     for (int i = 0; i < N; i++) v[i] = p[i * stride];
-    LeeIDCT<N>::run(v);
+    RefIDCT<N>::run(v, CosLut());
 #pragma unroll
     for (int i = 0; i < N; i++) p[i * stride] = v[i];
 }
@@ -285,23 +280,28 @@ __global__ void __launch_bounds__(256) k1_medium(K1Params P, const Sched *__rest
 
 // ------------------------------------------------------------------------------------------------------------
 // k1_big: 32-line strips of varblocks with a side >= 64.  PASS 0 = columns (reads coefficients, writes the plane),
-// PASS 1 = rows (reads the plane, writes the plane).  N = line length, R = N / 32 sub-sequences per line.
-// Shared memory: A[3][N][33] (inputs; output staging in pass 1), T[3][N][33] (R_32 results), llf scratch 3*32*33.
+// PASS 1 = rows (reads the plane, writes the plane).  N = line length.
+// MathHelper.inverseDCTHorizontal's recurrence, lane = line: a warp owns outputs k0..k0+15 and their mirrors
+// N-1-k of 32 lines (32 accumulators per lane), walks n = 1..N-1 reading in[n] from shared memory and the 16 table
+// entries lut[n-1][k0..k0+15] as four warp-uniform 128-bit loads, and skips n when in[n] is zero on all 32 lines
+// (adding +-0 products changes nothing; the coefficient rows of pass 0 are mostly zero).
+// Shared memory: A float[3][N][33] (inputs), T float[3][N][33] (pass 1 output staging), llf scratch float[3][32][33].
 // ------------------------------------------------------------------------------------------------------------
 #define BIG_PITCH 33
-template <int N> struct BigSmem {
+#define BIG_THREADS 256
+template <int N, int PASS> struct BigSmem {
     static constexpr int kA = 3 * N * BIG_PITCH;
-    static constexpr int kFloats = (N > 32 ? 2 * kA : kA) + 3 * 32 * BIG_PITCH;
+    static constexpr int kFloats = kA + (PASS == 1 ? kA : 0) + (PASS == 0 ? 3 * 32 * BIG_PITCH : 0);
     static constexpr int kBytes = kFloats * 4;
 };
+__host__ __device__ constexpr int cos_big_off(int n) { return n == 64 ? 0 : n == 128 ? 63 * 64 : 63 * 64 + 127 * 128; }
+#define COS_BIG_FLOATS (63 * 64 + 127 * 128 + 255 * 256)
 
-template <int N, int PASS> __global__ void __launch_bounds__(384) k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
+template <int N, int PASS> __global__ void __launch_bounds__(BIG_THREADS) k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
     extern __shared__ float smem[];
-    constexpr int R = N / 32;
-    constexpr int L = (N == 32 ? 0 : N == 64 ? 1 : N == 128 ? 2 : 3);
     float *A = smem;
-    float *T = smem + (N > 32 ? BigSmem<N>::kA : 0);
-    float *scr = smem + (N > 32 ? 2 * BigSmem<N>::kA : BigSmem<N>::kA);
+    float *T = smem + BigSmem<N, PASS>::kA;     // PASS 1 only
+    float *scr = smem + BigSmem<N, PASS>::kA;   // PASS 0 only
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int total = S->big_cum[PASS][cls][3];
@@ -378,7 +378,7 @@ template <int N, int PASS> __global__ void __launch_bounds__(384) k1_big(K1Param
                 float vv[32];
 #pragma unroll
                 for (int m = 0; m < 32; m++) vv[m] = A[(c * N + m) * BIG_PITCH + lane];
-                LeeIDCT<32>::run(vv);
+                RefIDCT<32>::run(vv, CosLut());
                 if (PASS == 0) {
 #pragma unroll
                     for (int m = 0; m < 32; m++)
@@ -389,42 +389,62 @@ template <int N, int PASS> __global__ void __launch_bounds__(384) k1_big(K1Param
                 }
             }
         } else {
-            // split: (channel, path) per warp, lane = line
-            for (int w = warp; w < 3 * R; w += nwarps) {
-                const int c = w / R, path = w % R;
+            const float *__restrict__ lut = P.cos_big + cos_big_off(N);
+            for (int w = warp; w < 3 * (N / 32); w += nwarps) {
+                const int c = w / (N / 32), k0 = (w % (N / 32)) * 16;
                 const float *src = A + (c * N) * BIG_PITCH + lane;
-                float vv[32];
+                float lo[16], hi[16];
+                const float in0 = src[0];
 #pragma unroll
-                for (int m = 0; m < 32; m++)
-                    vv[m] = LeeGather<L>::get([src](int i) { return src[i * BIG_PITCH]; }, path, m);
-                LeeIDCT<32>::run(vv);
+                for (int q = 0; q < 16; q++) { lo[q] = in0; hi[q] = in0; }
+#pragma unroll 2
+                for (int n = 1; n < N; n++) {
+                    const float s2 = src[n * BIG_PITCH];
+                    if (__ballot_sync(0xffffffffu, s2 != 0.0f) == 0u) continue;
+                    const float4 *lv = reinterpret_cast<const float4 *>(lut + (n - 1) * N + k0);
+                    float l[16];
 #pragma unroll
-                for (int m = 0; m < 32; m++) T[(c * N + path * 32 + m) * BIG_PITCH + lane] = vv[m];
-            }
-            __syncthreads();
-            // combine: (channel, k0) per warp
-            for (int w = warp; w < 3 * 32; w += nwarps) {
-                const int c = w / 32, k0 = w % 32;
-                float val[R];
-                int idx[R];
+                    for (int q = 0; q < 4; q++) {
+                        const float4 t4 = __ldg(lv + q);
+                        l[4 * q] = t4.x; l[4 * q + 1] = t4.y; l[4 * q + 2] = t4.z; l[4 * q + 3] = t4.w;
+                    }
+                    if (n & 1) {
 #pragma unroll
-                for (int p = 0; p < R; p++) val[p] = T[(c * N + p * 32 + k0) * BIG_PITCH + lane];
-                lee_combine<L>(val, idx, k0, SecDev());
+                        for (int q = 0; q < 16; q++) {
+                            const float p = __fmul_rn(s2, l[q]);
+                            lo[q] = __fadd_rn(lo[q], p);
+                            hi[q] = __fsub_rn(hi[q], p);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float p = __fmul_rn(s2, l[q]);
+                            lo[q] = __fadd_rn(lo[q], p);
+                            hi[q] = __fadd_rn(hi[q], p);
+                        }
+                    }
+                }
                 if (PASS == 0) {
 #pragma unroll
-                    for (int s = 0; s < R; s++)
-                        P.out[c][(size_t)(Y0 + idx[s]) * P.out_pitch + X0 + strip * 32 + lane] = val[s];
+                    for (int q = 0; q < 16; q++) {
+                        P.out[c][(size_t)(Y0 + k0 + q) * P.out_pitch + X0 + strip * 32 + lane] = lo[q];
+                        P.out[c][(size_t)(Y0 + N - 1 - k0 - q) * P.out_pitch + X0 + strip * 32 + lane] = hi[q];
+                    }
                 } else {
 #pragma unroll
-                    for (int s = 0; s < R; s++) A[(c * N + idx[s]) * BIG_PITCH + lane] = val[s];
+                    for (int q = 0; q < 16; q++) {
+                        T[(c * N + k0 + q) * BIG_PITCH + lane] = lo[q];
+                        T[(c * N + N - 1 - k0 - q) * BIG_PITCH + lane] = hi[q];
+                    }
                 }
             }
         }
         if (PASS == 1) {
             __syncthreads();
+            const float *O = N == 32 ? A : T;
             for (int i = tid; i < 3 * 32 * N; i += nt) {
                 const int c = i / (32 * N), r = (i / N) % 32, x = i % N;
-                P.out[c][(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x] = A[(c * N + x) * BIG_PITCH + r];
+                P.out[c][(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x] = O[(c * N + x) * BIG_PITCH + r];
             }
         }
         __syncthreads();

@@ -50,9 +50,11 @@ __global__ void k2_gab(K2Params P, const float *const in0, const float *const in
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *R = in[c] + (long long)r * in_pitch, *N = in[c] + (long long)rn * in_pitch, *S = in[c] + (long long)rs * in_pitch;
-        const float adj = R[xw] + R[xe] + N[x] + S[x];
-        const float diag = N[xw] + N[xe] + S[xw] + S[xe];
-        out[c][(long long)r * out_pitch + x] = P.gab_base[c] * R[x] + P.gab_adj[c] * adj + P.gab_diag[c] * diag;
+        // Frame.java:535-537, operand order kept, no FMA contraction -> bit-identical to the Java
+        const float adj = __fadd_rn(__fadd_rn(__fadd_rn(R[xw], R[xe]), N[x]), S[x]);
+        const float diag = __fadd_rn(__fadd_rn(__fadd_rn(N[xw], N[xe]), S[xw]), S[xe]);
+        out[c][(long long)r * out_pitch + x] = __fadd_rn(__fadd_rn(__fmul_rn(P.gab_base[c], R[x]), __fmul_rn(P.gab_adj[c], adj)),
+                                                         __fmul_rn(P.gab_diag[c], diag));
     }
 }
 
@@ -80,7 +82,6 @@ template <int PASS> __global__ void k2_epf(K2Params P, const float *in0, const f
     const int px[5] = {0, -1, 1, 0, 0};
     const int my = r & 7, mx = x & 7;
     const bool border = my == 0 || my == 7 || mx == 0 || mx == 7;
-    const float k = P.sigma_scale[PASS] * s;
     float sumW = 0.0f, sum[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int i = 0; i < NC; i++) {
@@ -89,42 +90,45 @@ template <int PASS> __global__ void k2_epf(K2Params P, const float *in0, const f
         for (int c = 0; c < 3; c++) {
             if (PASS == 2) {
                 const int dr = mirror_row(r + cy[i], P.rows, P.has_top, P.has_bottom), dc = mirror_col(x + cx[i], P.W);
-                dist += fabsf(in[c][o] - in[c][(long long)dr * pitch + dc]) * P.ch_scale[c];
+                dist = __fadd_rn(dist, __fmul_rn(fabsf(__fsub_rn(in[c][o], in[c][(long long)dr * pitch + dc])), P.ch_scale[c]));
             } else {
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
                     const int pr = mirror_row(r + py[j], P.rows, P.has_top, P.has_bottom), pc = mirror_col(x + px[j], P.W);
                     const int dr = mirror_row(r + cy[i] + py[j], P.rows, P.has_top, P.has_bottom), dc = mirror_col(x + cx[i] + px[j], P.W);
-                    dist += fabsf(in[c][(long long)pr * pitch + pc] - in[c][(long long)dr * pitch + dc]) * P.ch_scale[c];
+                    dist = __fadd_rn(dist, __fmul_rn(fabsf(__fsub_rn(in[c][(long long)pr * pitch + pc], in[c][(long long)dr * pitch + dc])), P.ch_scale[c]));
                 }
             }
         }
-        if (border) dist *= P.border_mul;
-        float w = 1.0f - dist * P.sigma_scale[PASS] * s;
+        if (border) dist = __fmul_rn(dist, P.border_mul);
+        float w = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(dist, P.sigma_scale[PASS]), s));   // epfWeight :677
         w = w < 0.0f ? 0.0f : w;
-        sumW += w;
+        sumW = __fadd_rn(sumW, w);
         const int nr = mirror_row(r + cy[i], P.rows, P.has_top, P.has_bottom), nc = mirror_col(x + cx[i], P.W);
 #pragma unroll
-        for (int c = 0; c < 3; c++) sum[c] += in[c][(long long)nr * pitch + nc] * w;
+        for (int c = 0; c < 3; c++) sum[c] = __fadd_rn(sum[c], __fmul_rn(in[c][(long long)nr * pitch + nc], w));
     }
-    (void)k;
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[c][o] = sum[c] / sumW;
+    for (int c = 0; c < 3; c++) out[c][o] = __fdiv_rn(sum[c], sumW);
 }
 
 __device__ __forceinline__ void color_px(const K2Params &P, float &a, float &b, float &c) {
     if (P.color_mode & 1) {
-        const float gl = b + a + P.cob[0], gm = b - a + P.cob[1], gs = c + P.cob[2];
-        const float ml = (gl * gl) * gl + P.ob[0], mm = (gm * gm) * gm + P.ob[1], ms = (gs * gs) * gs + P.ob[2];
-        a = P.m[0] * ml + P.m[1] * mm + P.m[2] * ms;
-        b = P.m[3] * ml + P.m[4] * mm + P.m[5] * ms;
-        c = P.m[6] * ml + P.m[7] * mm + P.m[8] * ms;
+        // OpsinInverseMatrix.invertXYB :128-138 with the Java's operation order and no FMA contraction: the matrix rows
+        // cancel to ~1e-3 of their terms on saturated colours, so a fused multiply-add here is visible at 16 bits
+        const float gl = __fadd_rn(__fadd_rn(b, a), P.cob[0]), gm = __fadd_rn(__fsub_rn(b, a), P.cob[1]), gs = __fadd_rn(c, P.cob[2]);
+        const float ml = __fadd_rn(__fmul_rn(__fmul_rn(gl, gl), gl), P.ob[0]);
+        const float mm = __fadd_rn(__fmul_rn(__fmul_rn(gm, gm), gm), P.ob[1]);
+        const float ms = __fadd_rn(__fmul_rn(__fmul_rn(gs, gs), gs), P.ob[2]);
+        a = __fadd_rn(__fadd_rn(__fmul_rn(P.m[0], ml), __fmul_rn(P.m[1], mm)), __fmul_rn(P.m[2], ms));
+        b = __fadd_rn(__fadd_rn(__fmul_rn(P.m[3], ml), __fmul_rn(P.m[4], mm)), __fmul_rn(P.m[5], ms));
+        c = __fadd_rn(__fadd_rn(__fmul_rn(P.m[6], ml), __fmul_rn(P.m[7], mm)), __fmul_rn(P.m[8], ms));
     }
     if (P.color_mode & 2) {
-        const float cb = a, yh = b + 0.50196078431372549019f, cr = c;
-        a = yh + 1.402f * cr;
-        b = yh - 0.34413628620102214650f * cb - 0.71413628620102214650f * cr;
-        c = yh + 1.772f * cb;
+        const float cb = a, yh = __fadd_rn(b, 0.50196078431372549019f), cr = c;
+        a = __fadd_rn(yh, __fmul_rn(1.402f, cr));
+        b = __fsub_rn(__fsub_rn(yh, __fmul_rn(0.34413628620102214650f, cb)), __fmul_rn(0.71413628620102214650f, cr));
+        c = __fadd_rn(yh, __fmul_rn(1.772f, cb));
     }
 }
 

@@ -4,115 +4,77 @@
 // box (no GPU needed) against the oracle before it ever reaches a B200.
 //
 // What the reference computes (J/ = /root/reference/java/com/traneptora/jxlatte/):
-//   1-D:  out[k] = in[0] + sum_{n>=1} in[n] * sqrt2 * cos(pi n (k + 1/2) / N)      J/util/MathHelper.java:68-78
-// jxlatte evaluates that as an O(N^2) sum; here it is Lee's recursive factorisation (even / pre-added-odd halves,
-// one secant multiply per butterfly), O(N log N), fully unrolled in registers for N <= 32.  Bigger N are split in
-// shared memory by lee_gather() / lee_combine() around the 32-point register kernel.
+//   1-D:  out[k] = in[0] + sum_{n>=1} in[n] * lut[n-1][k],  lut = (float)(sqrt2 cos(pi n (k + 1/2) / N))   J/util/MathHelper.java:17-30, 68-78
+//
+// The CUDA path evaluates exactly that sum: same products, same order of float additions per output, no FMA
+// contraction -> the XYB planes are bit-identical to the Java's.  A fast O(N log N) factorisation (Lee, even in
+// double) was measured and rejected: it differs from the Java by the Java's own accumulated rounding (X 4e-8, Y 7e-7
+// on DCT64+ blocks), and 3e-8 on X already moves a saturated dark pixel by more than one 16-bit sRGB step because
+// the opsin matrix rows cancel to 1e-3 of their terms there.  RefIDCT<N> is the register version for N <= 32; lines of
+// 64/128/256 use the same recurrence with the table in global memory (k1_idct.cuh, k1_big).
 #pragma once
 #include <math.h>
 
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #define JXLB_HD __host__ __device__ __forceinline__
+#define JXLB_MUL(a, b) __fmul_rn((a), (b))
+#define JXLB_ADD(a, b) __fadd_rn((a), (b))
+#define JXLB_SUB(a, b) __fsub_rn((a), (b))
+#elif defined(__CUDACC__)
+#define JXLB_HD __host__ __device__ __forceinline__
+#define JXLB_MUL(a, b) ((a) * (b))
+#define JXLB_ADD(a, b) ((a) + (b))
+#define JXLB_SUB(a, b) ((a) - (b))
 #else
 #define JXLB_HD inline
+#define JXLB_MUL(a, b) ((a) * (b))   /* host test build uses -ffp-contract=off */
+#define JXLB_ADD(a, b) ((a) + (b))
+#define JXLB_SUB(a, b) ((a) - (b))
 #endif
 
-#define JXLB_SQRT2 1.41421356237309504880f
+// offset of level log2(N) in the packed cosine LUT (levels 1..5 = lengths 2..32): sum_{j<l} (2^j - 1) 2^j
+JXLB_HD constexpr int cos_lut_off(int n) { return n == 2 ? 0 : n == 4 ? 2 : n == 8 ? 14 : n == 16 ? 70 : 310; }
 
-template <int N> JXLB_HD float lee_sec(int k);
-#include "idct_tables.cuh"
-
-// R_N: reference-convention inverse DCT of v[0..N), in place.
-template <int N> struct LeeIDCT {
-    static JXLB_HD void run(float *v) {
-        float e[N / 2], o[N / 2];
+// MathHelper.inverseDCTHorizontal (:68-78): same products, same order of additions per output.  The float table is
+// exactly antisymmetric/symmetric, lut[n-1][N-1-k] == (-1)^n lut[n-1][k] (checked when the tables are built), so each
+// product is formed once and added to out[k] and added to / subtracted from out[N-1-k]: bit-identical, 25% fewer ops.
+template <int N> struct RefIDCT {
+    template <class Lut> static JXLB_HD void run(float *v, Lut lut) {
+        float o[N];
 #pragma unroll
-        for (int i = 0; i < N / 2; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        for (int k = 0; k < N; k++) o[k] = v[0];
 #pragma unroll
-        for (int i = N / 2 - 1; i >= 1; i--) o[i] += o[i - 1];
-        o[0] *= JXLB_SQRT2;
-        LeeIDCT<N / 2>::run(e);
-        LeeIDCT<N / 2>::run(o);
+        for (int n = 1; n < N; n++) {
+            const float s2 = v[n];
 #pragma unroll
-        for (int k = 0; k < N / 2; k++) {
-            const float s = lee_sec<N>(k);
-            v[k] = fmaf(s, o[k], e[k]);
-            v[N - 1 - k] = fmaf(-s, o[k], e[k]);
-        }
-    }
-};
-template <> struct LeeIDCT<2> {
-    static JXLB_HD void run(float *v) { const float a = v[0], b = v[1]; v[0] = a + b; v[1] = a - b; }
-};
-template <> struct LeeIDCT<1> {
-    static JXLB_HD void run(float *) {}
-};
-
-// ---- splitting a long line (N = 32 * 2^L) around the 32-point register kernel ------------------------------
-// s_0 = X;  s_{l+1}[m] = b_l ? (m ? s_l[2m+1] + s_l[2m-1] : sqrt2 * s_l[1]) : s_l[2m];   b_l = bit l of path.
-// lee_gather<L>(in, path, m) = s_L[m]: element m of the 32-point sub-sequence selected by `path`.
-template <int L> struct LeeGather {
-    template <class In> static JXLB_HD float get(In in, int path, int m) {
-        const int b = (path >> (L - 1)) & 1;
-        if (!b) return LeeGather<L - 1>::get(in, path, 2 * m);
-        if (m == 0) return JXLB_SQRT2 * LeeGather<L - 1>::get(in, path, 1);
-        return LeeGather<L - 1>::get(in, path, 2 * m + 1) + LeeGather<L - 1>::get(in, path, 2 * m - 1);
-    }
-};
-template <> struct LeeGather<0> {
-    template <class In> static JXLB_HD float get(In in, int, int m) { return in(m); }
-};
-
-// lee_combine<L>: val[p] = R_32(sub-sequence p)[k0] for the R = 2^L paths; on return val[s] is output sample
-// idx[s] of the full N-point transform (s = 0..R-1).  sec(n, k) = 1 / (2 cos(pi (2k+1) / (2n))).
-template <int L, class Sec> JXLB_HD void lee_combine(float *val, int *idx, int k0, Sec sec) {
-    constexpr int R = 1 << L;
-    idx[0] = k0;
-#pragma unroll
-    for (int j = 0; j < L; j++) {
-        const int n2 = 64 << j;          // length after this combine
-        const int nseq = R >> j;         // sequences before this combine, each holding (1 << j) samples
-        const int ns = 1 << j;
-        float nv[R];
-        int ni[R];
-#pragma unroll
-        for (int pre = 0; pre < nseq / 2; pre++) {
-#pragma unroll
-            for (int s = 0; s < ns; s++) {
-                const float g = val[pre * ns + s];
-                const float h = val[(pre + nseq / 2) * ns + s];
-                const int ki = idx[s];
-                const float sc = sec(n2, ki);
-                nv[pre * 2 * ns + 2 * s] = fmaf(sc, h, g);
-                nv[pre * 2 * ns + 2 * s + 1] = fmaf(-sc, h, g);
-                ni[2 * s] = ki;
-                ni[2 * s + 1] = n2 - 1 - ki;
+            for (int k = 0; k < N / 2; k++) {
+                const float p = JXLB_MUL(s2, lut(cos_lut_off(N) + (n - 1) * N + k));
+                o[k] = JXLB_ADD(o[k], p);
+                o[N - 1 - k] = (n & 1) ? JXLB_SUB(o[N - 1 - k], p) : JXLB_ADD(o[N - 1 - k], p);
             }
         }
 #pragma unroll
-        for (int i = 0; i < R; i++) val[i] = nv[i];
-#pragma unroll
-        for (int i = 0; i < 2 * ns; i++) idx[i] = ni[i];
+        for (int k = 0; k < N; k++) v[k] = o[k];
     }
-}
+};
 
 // ---- 8x8-class varblocks: v[64] (row-major dequantised coefficients, LLF already in v[0]) -> out(y, x, value) ----
-// All follow J/frame/group/PassGroup.java:88-168, 227-325 statement by statement; only the 4/8-point DCTs inside are Lee.
+// All follow J/frame/group/PassGroup.java:88-168, 227-325 statement by statement, with explicit (uncontracted) float ops.
 
 // METHOD_DCT 8x8  (PassGroup.java:230-233 -> MathHelper.inverseDCT2D :96-122, columns then rows)
-template <class Out> JXLB_HD void inv_dct8x8(float *v, Out out) {
+template <class Lut, class Out> JXLB_HD void inv_dct8x8(float *v, Lut lut, Out out) {
 #pragma unroll
     for (int x = 0; x < 8; x++) {
         float c[8];
 #pragma unroll
         for (int y = 0; y < 8; y++) c[y] = v[y * 8 + x];
-        LeeIDCT<8>::run(c);
+        RefIDCT<8>::run(c, lut);
 #pragma unroll
         for (int y = 0; y < 8; y++) v[y * 8 + x] = c[y];
     }
 #pragma unroll
     for (int y = 0; y < 8; y++) {
-        LeeIDCT<8>::run(v + y * 8);
+        RefIDCT<8>::run(v + y * 8, lut);
 #pragma unroll
         for (int x = 0; x < 8; x++) out(y, x, v[y * 8 + x]);
     }
@@ -120,10 +82,10 @@ template <class Out> JXLB_HD void inv_dct8x8(float *v, Out out) {
 
 // 2x2 Hadamard of PassGroup.auxDCT2 (:154-165), operand order kept
 JXLB_HD void aux2x2(float c00, float c01, float c10, float c11, float &r00, float &r01, float &r10, float &r11) {
-    r00 = c00 + c01 + c10 + c11;
-    r01 = c00 + c01 - c10 - c11;
-    r10 = c00 - c01 + c10 - c11;
-    r11 = c00 - c01 - c10 + c11;
+    r00 = JXLB_ADD(JXLB_ADD(JXLB_ADD(c00, c01), c10), c11);
+    r01 = JXLB_SUB(JXLB_SUB(JXLB_ADD(c00, c01), c10), c11);
+    r10 = JXLB_SUB(JXLB_ADD(JXLB_SUB(c00, c01), c10), c11);
+    r11 = JXLB_ADD(JXLB_SUB(JXLB_SUB(c00, c01), c10), c11);
 }
 
 // METHOD_DCT2  (PassGroup.java:273-277): auxDCT2 with s = 2, 4, 8
@@ -166,21 +128,21 @@ template <class Out> JXLB_HD void inv_hornuss(const float *v, Out out) {
 #pragma unroll
             for (int iy = 0; iy < 4; iy++)
 #pragma unroll
-                for (int ix = (iy == 0 ? 1 : 0); ix < 4; ix++) residual += v[(y + iy * 2) * 8 + x + ix * 2];
-            const float centre = blockLF - residual * 0.0625f;
+                for (int ix = (iy == 0 ? 1 : 0); ix < 4; ix++) residual = JXLB_ADD(residual, v[(y + iy * 2) * 8 + x + ix * 2]);
+            const float centre = JXLB_SUB(blockLF, JXLB_MUL(residual, 0.0625f));
 #pragma unroll
             for (int iy = 0; iy < 4; iy++)
 #pragma unroll
                 for (int ix = 0; ix < 4; ix++) {
                     if (ix == 1 && iy == 1) out(4 * y + 1, 4 * x + 1, centre);
-                    else if (ix == 0 && iy == 0) out(4 * y, 4 * x, v[(y + 2) * 8 + x + 2] + centre);
-                    else out(y * 4 + iy, x * 4 + ix, v[(y + iy * 2) * 8 + x + ix * 2] + centre);
+                    else if (ix == 0 && iy == 0) out(4 * y, 4 * x, JXLB_ADD(v[(y + 2) * 8 + x + 2], centre));
+                    else out(y * 4 + iy, x * 4 + ix, JXLB_ADD(v[(y + iy * 2) * 8 + x + ix * 2], centre));
                 }
         }
 }
 
 // METHOD_DCT4  (PassGroup.java:306-325): four 4x4 IDCTs, transposed = true
-template <class Out> JXLB_HD void inv_dct4(const float *v, Out out) {
+template <class Lut, class Out> JXLB_HD void inv_dct4(const float *v, Lut lut, Out out) {
     float lf[4];
     aux2x2(v[0], v[1], v[8], v[9], lf[0], lf[1], lf[2], lf[3]);
 #pragma unroll
@@ -194,11 +156,11 @@ template <class Out> JXLB_HD void inv_dct4(const float *v, Out out) {
                 for (int ix = 0; ix < 4; ix++) b[iy * 4 + ix] = v[(y + iy * 2) * 8 + x + ix * 2];
             b[0] = lf[y * 2 + x];
 #pragma unroll
-            for (int iy = 0; iy < 4; iy++) LeeIDCT<4>::run(b + iy * 4);   // over ix -> k
+            for (int iy = 0; iy < 4; iy++) RefIDCT<4>::run(b + iy * 4, lut);   // over ix -> k
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 float c[4] = {b[k], b[4 + k], b[8 + k], b[12 + k]};        // over iy -> m
-                LeeIDCT<4>::run(c);
+                RefIDCT<4>::run(c, lut);
 #pragma unroll
                 for (int m = 0; m < 4; m++) out(4 * y + k, 4 * x + m, c[m]);
             }
@@ -207,9 +169,9 @@ template <class Out> JXLB_HD void inv_dct4(const float *v, Out out) {
 
 // METHOD_DCT8_4 (TransformType.DCT8_4, PassGroup.java:234-251): two 4x8 coefficient sets, transposed = true
 // -> two 8-row x 4-col halves side by side.  METHOD_DCT4_8 (:252-269): transposed = false -> two 4x8 halves stacked.
-template <bool kTransposed, class Out> JXLB_HD void inv_dct4x8(const float *v, Out out) {
+template <bool kTransposed, class Lut, class Out> JXLB_HD void inv_dct4x8(const float *v, Lut lut, Out out) {
     const float coeff0 = v[0], coeff1 = v[8];
-    const float lfs[2] = {coeff0 + coeff1, coeff0 - coeff1};
+    const float lfs[2] = {JXLB_ADD(coeff0, coeff1), JXLB_SUB(coeff0, coeff1)};
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         float b[32];
@@ -220,11 +182,11 @@ template <bool kTransposed, class Out> JXLB_HD void inv_dct4x8(const float *v, O
         b[0] = lfs[h];
         if (kTransposed) {
 #pragma unroll
-            for (int iy = 0; iy < 4; iy++) LeeIDCT<8>::run(b + iy * 8);  // over ix -> k (pixel row)
+            for (int iy = 0; iy < 4; iy++) RefIDCT<8>::run(b + iy * 8, lut);  // over ix -> k (pixel row)
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 float c[4] = {b[k], b[8 + k], b[16 + k], b[24 + k]};      // over iy -> m (pixel column)
-                LeeIDCT<4>::run(c);
+                RefIDCT<4>::run(c, lut);
 #pragma unroll
                 for (int m = 0; m < 4; m++) out(k, 4 * h + m, c[m]);
             }
@@ -232,12 +194,12 @@ template <bool kTransposed, class Out> JXLB_HD void inv_dct4x8(const float *v, O
 #pragma unroll
             for (int ix = 0; ix < 8; ix++) {
                 float c[4] = {b[ix], b[8 + ix], b[16 + ix], b[24 + ix]};  // columns first: over iy -> m
-                LeeIDCT<4>::run(c);
+                RefIDCT<4>::run(c, lut);
                 b[ix] = c[0]; b[8 + ix] = c[1]; b[16 + ix] = c[2]; b[24 + ix] = c[3];
             }
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-                LeeIDCT<8>::run(b + m * 8);                                // rows: over ix -> k
+                RefIDCT<8>::run(b + m * 8, lut);                                // rows: over ix -> k
 #pragma unroll
                 for (int k = 0; k < 8; k++) out(4 * h + m, k, b[m * 8 + k]);
             }
@@ -246,20 +208,20 @@ template <bool kTransposed, class Out> JXLB_HD void inv_dct4x8(const float *v, O
 }
 
 // METHOD_AFV  (PassGroup.invertAFV :88-147).  basis(j, i) = AFV_BASIS[j][i] (:19-58).
-template <class Basis, class Out> JXLB_HD void inv_afv(const float *v, int flipY, int flipX, Basis basis, Out out) {
+template <class Basis, class Lut, class Out> JXLB_HD void inv_afv(const float *v, int flipY, int flipX, Basis basis, Lut lut, Out out) {
     float a[16];
 #pragma unroll
     for (int iy = 0; iy < 4; iy++)
 #pragma unroll
         for (int ix = 0; ix < 4; ix++) a[iy * 4 + ix] = v[(iy * 2) * 8 + ix * 2];
-    a[0] = (v[0] + v[8] + v[1]) * 4.0f;
+    a[0] = JXLB_MUL(JXLB_ADD(JXLB_ADD(v[0], v[8]), v[1]), 4.0f);
 #pragma unroll
     for (int iy = 0; iy < 4; iy++)
 #pragma unroll
         for (int ix = 0; ix < 4; ix++) {
             float sample = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 16; j++) sample += a[j] * basis(j, iy * 4 + ix);
+            for (int j = 0; j < 16; j++) sample = JXLB_ADD(sample, JXLB_MUL(a[j], basis(j, iy * 4 + ix)));
             // scratch[1][iy][ix] lands at buffer[flipY*4 + (flipY ? 3-iy : iy)][flipX*4 + (flipX ? 3-ix : ix)]
             out(flipY * 4 + (flipY ? 3 - iy : iy), flipX * 4 + (flipX ? 3 - ix : ix), sample);
         }
@@ -268,16 +230,16 @@ template <class Basis, class Out> JXLB_HD void inv_afv(const float *v, int flipY
     for (int iy = 0; iy < 4; iy++)
 #pragma unroll
         for (int ix = 0; ix < 4; ix++) a[iy * 4 + ix] = v[(iy * 2) * 8 + ix * 2 + 1];
-    a[0] = v[0] + v[8] - v[1];
+    a[0] = JXLB_SUB(JXLB_ADD(v[0], v[8]), v[1]);
     {   // inverseDCT2D(4x4, transposed = false): columns (over iy) then rows (over ix)
 #pragma unroll
         for (int ix = 0; ix < 4; ix++) {
             float c[4] = {a[ix], a[4 + ix], a[8 + ix], a[12 + ix]};
-            LeeIDCT<4>::run(c);
+            RefIDCT<4>::run(c, lut);
             a[ix] = c[0]; a[4 + ix] = c[1]; a[8 + ix] = c[2]; a[12 + ix] = c[3];
         }
 #pragma unroll
-        for (int iy = 0; iy < 4; iy++) LeeIDCT<4>::run(a + iy * 4);
+        for (int iy = 0; iy < 4; iy++) RefIDCT<4>::run(a + iy * 4, lut);
     }
 #pragma unroll
     for (int iy = 0; iy < 4; iy++)
@@ -289,16 +251,16 @@ template <class Basis, class Out> JXLB_HD void inv_afv(const float *v, int flipY
     for (int iy = 0; iy < 4; iy++)
 #pragma unroll
         for (int ix = 0; ix < 8; ix++) b[iy * 8 + ix] = v[(1 + iy * 2) * 8 + ix];
-    b[0] = v[0] - v[8];
+    b[0] = JXLB_SUB(v[0], v[8]);
 #pragma unroll
     for (int ix = 0; ix < 8; ix++) {
         float c[4] = {b[ix], b[8 + ix], b[16 + ix], b[24 + ix]};
-        LeeIDCT<4>::run(c);
+        RefIDCT<4>::run(c, lut);
         b[ix] = c[0]; b[8 + ix] = c[1]; b[16 + ix] = c[2]; b[24 + ix] = c[3];
     }
 #pragma unroll
     for (int iy = 0; iy < 4; iy++) {
-        LeeIDCT<8>::run(b + iy * 8);
+        RefIDCT<8>::run(b + iy * 8, lut);
 #pragma unroll
         for (int ix = 0; ix < 8; ix++) out((flipY ? 0 : 4) + iy, ix, b[iy * 8 + ix]);
     }

@@ -118,6 +118,9 @@ class Reconstructor:
     def launch_count(self):
         return int(self._L.jxlb200_launch_count(self._h))
 
+    def set_option(self, option, value):
+        self._check(self._L.jxlb200_set_option(self._h, int(option), int(value)))
+
     # -- HFGlobal --
     def generateWeights(self, prm=None):
         w, off = qm_generate(prm)

@@ -52,8 +52,9 @@ class _Layout:
         self.dx[y:y + bh, x:x + bw] = np.arange(bw, dtype=np.int16)[None, :]
 
 
-def _fill_aligned(L, rng, y0, x0, size, probs):
-    """Recursive aligned subdivision of the size x size-cell square at (y0, x0)."""
+def _fill_aligned(L, rng, y0, x0, size, probs, force=None):
+    """Recursive aligned subdivision of the size x size-cell square at (y0, x0).  force = 0/1/2 picks the
+    square / two tall / two wide arrangement at this level unconditionally."""
     if y0 >= L.hb or x0 >= L.wb:
         return
     p8, p32, p64, p128, p256 = probs
@@ -62,8 +63,8 @@ def _fill_aligned(L, rng, y0, x0, size, probs):
         rest = [p256 + p128 + p64 + p32 + p8, p128 + p64 + p32 + p8, p64 + p32 + p8][level]
         take = [p256, p128, p64][level]
         sq, tall, wide = [(24, 25, 26), (21, 22, 23), (18, 19, 20)][level]
-        if rest > 0 and rng.random() < take / rest:
-            k = rng.integers(0, 3)
+        if force is not None or (rest > 0 and rng.random() < take / rest):
+            k = rng.integers(0, 3) if force is None else force
             half = size // 2
             cand = [[(y0, x0, sq)], [(y0, x0, tall), (y0, x0 + half, tall)], [(y0, x0, wide), (y0 + half, x0, wide)]][k]
             if all(L.fits(y, x, t) for (y, x, t) in cand):
@@ -127,7 +128,7 @@ def _fill_first_fit(L, rng, probs):
             L.put(y, x, t)
 
 
-def make_partition(hb, wb, rng, mix="mixed", aligned=True, bank=16):
+def make_partition(hb, wb, rng, mix="mixed", aligned=True, bank=27):
     """-> dct_select u8[hb,wb], block_origin u8[hb,wb], (oy, ox) int32 maps of each cell's varblock origin."""
     if mix == "dct8":
         ds = np.zeros((hb, wb), np.uint8)
@@ -135,10 +136,10 @@ def make_partition(hb, wb, rng, mix="mixed", aligned=True, bank=16):
         return ds, np.ones((hb, wb), np.uint8), oy.copy(), ox.copy()
     probs = MIXES[mix] if isinstance(mix, str) else tuple(mix)
 
-    def gen(h, w):
+    def gen(h, w, force=None):
         L = _Layout(h, w)
         if aligned:
-            _fill_aligned(L, rng, 0, 0, 32, probs)
+            _fill_aligned(L, rng, 0, 0, 32, probs, force)
         else:
             _fill_first_fit(L, rng, probs)
         assert (L.ds != 255).all()
@@ -147,6 +148,9 @@ def make_partition(hb, wb, rng, mix="mixed", aligned=True, bank=16):
     gh, gw = (hb + 31) // 32, (wb + 31) // 32
     n_full = (hb // 32) * (wb // 32)
     layouts = [gen(32, 32) for _ in range(min(bank, n_full))] if n_full else []
+    if aligned and probs[4] > 0 and n_full >= 24:
+        # a frame this large must contain all three 256-class kinds (DCT256, DCT256_128, DCT128_256)
+        layouts += [gen(32, 32, force=k) for k in range(3)]
     ds = np.zeros((hb, wb), np.uint8)
     dy = np.zeros((hb, wb), np.int32)
     dx = np.zeros((hb, wb), np.int32)

@@ -1,0 +1,51 @@
+"""Host logic above the C ABI: ModularStream channel bookkeeping and the multi-GPU partitioning."""
+import numpy as np
+
+from jxlatte_b200.host import default_squeeze_params, forward_channel_layout
+from jxlatte_b200.multigpu import slab_rows, frame_owner, split_state
+
+
+def test_default_squeeze_params_follow_modularstream():
+    # 3 channels of 64 x 48, no meta channels (ModularStream.java:110-131)
+    sp = default_squeeze_params([(48, 64)] * 3, 0)
+    assert sp[0] == (True, False, 1, 2) and sp[1] == (False, False, 1, 2)   # chroma first, not in place
+    rest = sp[2:]
+    assert rest[0] == (True, True, 0, 3)          # h < w: no leading vertical step
+    hs = sum(1 for s in rest if s[0])
+    vs = sum(1 for s in rest if not s[0])
+    assert hs == 3 and vs == 3                     # 64 -> 8 and 48 -> 6
+    # tall single channel: leading vertical step
+    sp = default_squeeze_params([(100, 10)], 0)
+    assert sp[0] == (False, True, 0, 1)
+
+
+def test_forward_channel_layout_shapes():
+    sizes = [(5, 9)]
+    out = forward_channel_layout(sizes, [(True, True, 0, 1), (False, True, 0, 1)])
+    # horizontal: (5, 5) + residual (5, 4); then vertical on channel 0: (3, 5) + residual (2, 5) inserted right after it
+    assert out == [(3, 5), (2, 5), (5, 4)]
+
+
+def test_slab_rows_partition_the_frame_by_group_rows():
+    for H in (256, 4320, 16384, 8, 4096 + 8):
+        for world in (1, 2, 3, 4, 8):
+            spans = [slab_rows(H, world, r) for r in range(world)]
+            assert spans[0][0] == 0
+            assert sum(r for _, r in spans) == H
+            for (y0, rows), (y1, _) in zip(spans, spans[1:]):
+                assert y0 + rows == y1
+            for y0, rows in spans:
+                assert y0 % 256 == 0 or rows == 0
+    assert slab_rows(16384, 8, 3) == (3 * 2048, 2048)
+
+
+def test_frame_owner_round_robin():
+    assert [frame_owner(i, 4) for i in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+def test_split_state_cuts_every_map_consistently():
+    from jxlatte_b200 import synth
+    st = synth.make_state(64, 512, seed=3, mix="dct8")
+    s = split_state(st, 256, 256)
+    assert s["qcoeff"].shape == (3, 256, 64) and s["lf"].shape == (3, 32, 8) and s["x_from_y"].shape == (4, 1)
+    assert np.array_equal(s["hf_mul"], st["hf_mul"][32:])

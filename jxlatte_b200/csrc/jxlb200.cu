@@ -12,6 +12,7 @@
 #include "k1_idct.cuh"
 #include "k2_restore.cuh"
 #include "k2_fused.cuh"
+#include "k2_exact.cuh"
 #include "k3_modular.cuh"
 #include "qm_tables.cuh"
 
@@ -121,7 +122,9 @@ int upload_constants(jxlb200_ctx *ctx) {
     CUDA_TRY(ctx, (big_attr<128, 0>())); CUDA_TRY(ctx, (big_attr<256, 0>()));
     CUDA_TRY(ctx, (big_attr<32, 1>()));  CUDA_TRY(ctx, (big_attr<64, 1>()));
     CUDA_TRY(ctx, (big_attr<128, 1>())); CUDA_TRY(ctx, (big_attr<256, 1>()));
-    return k2_fused_init(ctx);
+    CUDA_TRY(ctx, k2_fused_init_all());
+    CUDA_TRY(ctx, k2_exact_init_all());
+    return 0;
 }
 
 int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
@@ -244,13 +247,19 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                      ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-    if (ctx->opt_stage2 != 1 && k2_fused_supported(K)) {
-        int rc = k2_fused_launch(ctx, K, inv_sigma);
-        if (rc) return rc;
+    if (ctx->opt_stage2 == 0 && k2_exact_supported(K)) {          // default: fused, bit-exact
+        k2_exact_dispatch(K, inv_sigma, st);
+        ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
         return 0;
     }
-    if (ctx->opt_stage2 == 2) return ctx->fail(JXLB200_E_UNSUPPORTED, "fused stage 2 does not take this frame");
+    if (ctx->opt_stage2 == 2) {                                     // opt-in: fused with re-associated EPF sums
+        if (!k2_fused_supported(K)) return ctx->fail(JXLB200_E_UNSUPPORTED, "fused stage 2 does not take this frame");
+        k2_fused_dispatch(K, inv_sigma, st);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    }
 
     // ---- staged fallback-free path: one kernel per stage, planes ping-pong through ctx->pp ----
     const long long pp_pitch = W;

@@ -52,12 +52,12 @@ def test_cuda_reproduces_golden_frame(recon):
     from jxlatte_b200 import _lib
     p, st, xyb, out = _frame()
     assert np.array_equal(recon.invertVarDCT(p, st), xyb)
+    assert np.array_equal(recon.reconstruct(p, st), out)          # default: fused exact kernel
     recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_STAGED)
     try:
         assert np.array_equal(recon.reconstruct(p, st), out)
     finally:
         recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
-    assert np.abs(recon.reconstruct(p, st) - out).max() <= 1e-4
 
 
 @pytest.mark.gpu

@@ -73,7 +73,7 @@ def test_gaborish(recon, orc):
     planes = rng.random((3, 200, 328), dtype=np.float32)
     ref = orc.gab(p, planes)
     got = recon.performGabConvolution(p, planes)
-    assert np.abs(got - ref).max() <= 1e-6
+    assert np.array_equal(got, ref)
     recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_STAGED)
     try:
         assert np.array_equal(recon.performGabConvolution(p, planes), ref)
@@ -92,12 +92,14 @@ def test_epf(recon, orc, iters):
     sh = rng.integers(0, 8, size=(H // 8, W // 8)).astype(np.int32)   # includes 0 = pass-through blocks
     ref = orc.epf(p, planes, hm, sh, nthreads=8)
     got = recon.performEdgePreservingFilter(p, planes, hm, sh)
-    assert np.abs(got - ref).max() <= 5e-6
-    recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_STAGED)
-    try:
-        assert np.array_equal(recon.performEdgePreservingFilter(p, planes, hm, sh), ref)
-    finally:
-        recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
+    assert np.array_equal(got, ref), "max abs err %g" % np.abs(got - ref).max()
+    for opt, exact in ((_lib.STAGE2_STAGED, True), (_lib.STAGE2_FUSED, False)):
+        recon.set_option(_lib.OPT_STAGE2, opt)
+        try:
+            g2 = recon.performEdgePreservingFilter(p, planes, hm, sh)
+        finally:
+            recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
+        assert np.array_equal(g2, ref) if exact else np.abs(g2 - ref).max() <= 5e-6
 
 
 def test_epf_rejects_bad_sharpness(recon):
@@ -139,24 +141,29 @@ def _srgb_quantise(lin, bits):
     dict(shape=(264, 520), iters=0, gab=True),
     dict(shape=(256, 256), iters=0, gab=False),
 ])
-@pytest.mark.parametrize("stage2", ["staged", "auto"])
+@pytest.mark.parametrize("stage2", ["staged", "auto", "fast"])
 def test_full_reconstruction(recon, orc, cfg, stage2):
     W, H = cfg["shape"]
     p = default_frame_params(W, H, epf_iters=cfg["iters"], gab=cfg["gab"])
     st = _state(W, H, 11 + W, p)
     ref = orc.vardct_reconstruct(p, st, nthreads=8)
-    recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_STAGED if stage2 == "staged" else _lib.STAGE2_AUTO)
+    if stage2 == "fast" and not (cfg["gab"] or cfg["iters"]):
+        pytest.skip("nothing to fuse")
+    recon.set_option(_lib.OPT_STAGE2, {"staged": _lib.STAGE2_STAGED, "auto": _lib.STAGE2_AUTO, "fast": _lib.STAGE2_FUSED}[stage2])
     try:
         got = recon.reconstruct(p, st)
     finally:
         recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
-    if stage2 == "staged":
-        assert np.array_equal(got, ref), "staged path must be bit-identical; max abs err %g" % np.abs(got - ref).max()
+    if stage2 != "fast":
+        assert np.array_equal(got, ref), "%s path must be bit-identical; max abs err %g" % (stage2, np.abs(got - ref).max())
     err = np.abs(got - ref).max()
     assert err <= TOL_LINEAR, "max abs err %g on linear planes" % err
     for bits in (8, 16):
-        d = np.abs(_srgb_quantise(got, bits) - _srgb_quantise(ref, bits)).max()
-        assert d <= 1, "%d-bit sRGB differs by %d LSB" % (bits, d)
+        d = np.abs(_srgb_quantise(got, bits) - _srgb_quantise(ref, bits))
+        # the opt-in re-associated EPF may move saturated dark pixels by 2 steps at 16 bits (documented in the header)
+        lim = 2 if (stage2 == "fast" and bits == 16) else 1
+        assert d.max() <= lim, "%d-bit sRGB differs by %d LSB" % (bits, d.max())
+        assert (d > 1).mean() <= 1e-5
 
 
 def test_invalid_transform_type_is_reported(recon):

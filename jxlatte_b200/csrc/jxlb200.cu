@@ -70,7 +70,7 @@ const float kScaleF[32] = {
 };
 
 template <int N, int PASS> cudaError_t big_attr() {
-    return cudaFuncSetAttribute(k1_big<N, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigSmem<N, PASS>::kBytes);
+    return cudaFuncSetAttribute(k1_big<N, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BigCfg<N, PASS>::kBytes);
 }
 
 int upload_constants(jxlb200_ctx *ctx) {
@@ -142,8 +142,9 @@ int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
 }
 
 template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls) {
-    const int per_sm = max(1, min(4, (227 * 1024) / (BigSmem<N, PASS>::kBytes + 1024)));
-    k1_big<N, PASS><<<ctx->sms * per_sm, BIG_THREADS, BigSmem<N, PASS>::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
+    using Cfg = BigCfg<N, PASS>;
+    const int per_sm = max(1, min(min(2048 / Cfg::kThreads, 16), (227 * 1024) / (Cfg::kBytes + 1024)));
+    k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
     ctx->launches++;
 }
 

@@ -56,8 +56,8 @@ __global__ void k0_plan(Sched *s) {
                 const int t = c_big_types[pass][k][j];
                 if (t >= 0) {
                     const TTInfo tt = c_tt[t];
-                    // pass 0 walks 32-column strips (bw * 8 / 32 of them), pass 1 walks 32-row strips
-                    cum += s->cnt[t] * ((pass == 0 ? tt.bw : tt.bh) / 4);
+                    // pass 0 walks 32-column strips (bw * 8 / 32 of them), pass 1 walks 32-row strips; one item per channel
+                    cum += s->cnt[t] * ((pass == 0 ? tt.bw : tt.bh) / 4) * 3;
                 }
             }
             s->big_cum[pass][k][3] = cum;

@@ -279,29 +279,83 @@ __global__ void __launch_bounds__(256) k1_medium(K1Params P, const Sched *__rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k1_big: 32-line strips of varblocks with a side >= 64.  PASS 0 = columns (reads coefficients, writes the plane),
-// PASS 1 = rows (reads the plane, writes the plane).  N = line length.
-// MathHelper.inverseDCTHorizontal's recurrence, lane = line: a warp owns outputs k0..k0+15 and their mirrors
-// N-1-k of 32 lines (32 accumulators per lane), walks n = 1..N-1 reading in[n] from shared memory and the 16 table
-// entries lut[n-1][k0..k0+15] as four warp-uniform 128-bit loads, and skips n when in[n] is zero on all 32 lines
-// (adding +-0 products changes nothing; the coefficient rows of pass 0 are mostly zero).
-// Shared memory: A float[3][N][33] (inputs), T float[3][N][33] (pass 1 output staging), llf scratch float[3][32][33].
+// k1_big: varblocks with a side >= 64, two passes over 32-line strips, ONE CHANNEL per work item (a strip of one
+// channel is 8..32 KB of shared memory, so several CTAs share an SM and the tail of the launch is short).
+// PASS 0 = columns (reads coefficients, writes the plane), PASS 1 = rows (reads the plane, writes the plane).
+// N = line length.  Both passes evaluate MathHelper.inverseDCTHorizontal's recurrence
+//   out[k] = in[0] + sum_n fl(in[n] * lut[n-1][k])   in n order,
+// forming each product once for out[k] and out[N-1-k] (the float table is exactly (anti)symmetric).
+//   PASS 0  lane = column.  A warp owns outputs k0..k0+7 and their mirrors of 32 columns.  Coefficient rows that are
+//           zero on all 32 columns are dropped up front (adding +-0 products changes nothing and most rows are zero):
+//           the load phase flags live rows, a compaction builds the list, and the walk over the list reads in[n] from
+//           shared memory and lut[n-1][k0..k0+7] as two warp-uniform 128-bit loads issued one live row ahead.
+//           X and B items also dequantise Y (chroma-from-luma needs it).  Results go straight to the plane.
+//   PASS 1  lane = output index k (and its mirror).  A warp owns 32 k's of 16 rows: per n one coalesced table load
+//           (issued four n ahead) and four 128-bit shared-memory broadcasts of in[row][n]; results go straight to the
+//           plane, 128 bytes per row.
+// Shared memory per CTA: PASS 0  A float[N][33] + llf scratch float[32][33] + row flags;  PASS 1  A float[N][36].
 // ------------------------------------------------------------------------------------------------------------
 #define BIG_PITCH 33
-#define BIG_THREADS 256
-template <int N, int PASS> struct BigSmem {
-    static constexpr int kA = 3 * N * BIG_PITCH;
-    static constexpr int kFloats = kA + (PASS == 1 ? kA : 0) + (PASS == 0 ? 3 * 32 * BIG_PITCH : 0);
+#define BIG_PITCH1 36
+template <int N, int PASS> struct BigCfg {
+    static constexpr int kThreads = N == 32 ? 128 : (PASS == 0 ? 2 * N : N);
+    static constexpr int kFloats = PASS == 0 ? N * BIG_PITCH + 32 * BIG_PITCH + N / 4 + 4 : (N == 32 ? N * BIG_PITCH : N * BIG_PITCH1);
     static constexpr int kBytes = kFloats * 4;
 };
 __host__ __device__ constexpr int cos_big_off(int n) { return n == 64 ? 0 : n == 128 ? 63 * 64 : 63 * 64 + 127 * 128; }
 #define COS_BIG_FLOATS (63 * 64 + 127 * 128 + 255 * 256)
 
-template <int N, int PASS> __global__ void __launch_bounds__(BIG_THREADS) k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
+__device__ __forceinline__ void ld_lut8(const float *p, float (&l)[8]) {
+    const float4 *v = reinterpret_cast<const float4 *>(p);
+    const float4 a = __ldg(v), b = __ldg(v + 1);
+    l[0] = a.x; l[1] = a.y; l[2] = a.z; l[3] = a.w; l[4] = b.x; l[5] = b.y; l[6] = b.z; l[7] = b.w;
+}
+
+// One channel of a varblock: everything dequant_ch needs, fetched once per work item (c is a run-time value there)
+struct ChanCtx {
+    const int32_t *qc, *qy;      // this channel's and Y's coefficient planes
+    const float *wc, *wy;        // weights in storage orientation
+    const int32_t *fy;           // x_from_y or b_from_y
+    float sfc_c, sfc_y, qb_c, qb_y, base;
+    int c;
+};
+__device__ __forceinline__ ChanCtx make_chan(const K1Params &P, const VB &v, int c) {
+    ChanCtx k;
+    k.c = c;
+    k.qc = c == 0 ? P.q[0] : (c == 1 ? P.q[1] : P.q[2]);
+    k.qy = P.q[1];
+    k.wc = c == 0 ? v.w[0] : (c == 1 ? v.w[1] : v.w[2]);
+    k.wy = v.w[1];
+    k.fy = c == 0 ? P.xfy : P.bfy;
+    k.sfc_c = c == 0 ? v.sfc[0] : (c == 1 ? v.sfc[1] : v.sfc[2]);
+    k.sfc_y = v.sfc[1];
+    k.qb_c = c == 0 ? P.qb[0] : (c == 1 ? P.qb[1] : P.qb[2]);
+    k.qb_y = P.qb[1];
+    k.base = c == 0 ? P.base_x : P.base_b;
+    return k;
+}
+// dequantise + CfL one channel of the coefficient at local (ly, lx) (outside the LLF corner)
+__device__ __forceinline__ float dequant_ch(const K1Params &P, const VB &v, const ChanCtx &k, int ly, int lx) {
+    const int py = v.by * 8 + ly, px = v.bx * 8 + lx;
+    const size_t gi = (size_t)py * P.W + px;
+    const int wi = ly * v.W + lx;
+    const float Y = dequant_one(__ldg(k.qy + gi), k.qb_y, P.qbn, k.sfc_y, __ldg(k.wy + wi));
+    if (k.c == 1) return Y;
+    const float C = dequant_one(__ldg(k.qc + gi), k.qb_c, P.qbn, k.sfc_c, __ldg(k.wc + wi));
+    const int tile = (py >> 6) * P.tw + (px >> 6);
+    float f = 0.0f;   // chromaFromLuma :172-188, see dequant3
+    if (__ldg(P.cfl_gate + tile) <= v.origin) f = __fadd_rn(k.base, __fdiv_rn((float)__ldg(k.fy + tile), P.color_factor));
+    return __fadd_rn(C, __fmul_rn(f, Y));
+}
+
+template <int N, int PASS> __global__ void __launch_bounds__(BigCfg<N, PASS>::kThreads)
+k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
     extern __shared__ float smem[];
     float *A = smem;
-    float *T = smem + BigSmem<N, PASS>::kA;     // PASS 1 only
-    float *scr = smem + BigSmem<N, PASS>::kA;   // PASS 0 only
+    float *scr = smem + N * BIG_PITCH;   // PASS 0 only
+    unsigned char *rowflag = reinterpret_cast<unsigned char *>(scr + 32 * BIG_PITCH);
+    unsigned char *rowlist = reinterpret_cast<unsigned char *>(scr);   // valid once the LLF scratch is dead
+    int *rowcnt = reinterpret_cast<int *>(rowflag + N);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int total = S->big_cum[PASS][cls][3];
@@ -312,28 +366,31 @@ template <int N, int PASS> __global__ void __launch_bounds__(BIG_THREADS) k1_big
         const TTInfo tt = c_tt[type];
         const int nstrips = (PASS == 0 ? tt.bw : tt.bh) / 4;
         const int local = wi - S->big_cum[PASS][cls][j];
-        const int strip = local % nstrips;
-        const VB v = make_vb(P, items[S->start[type] + local / nstrips], type);
+        const int c = local % 3, strip = (local / 3) % nstrips;
+        const VB v = make_vb(P, items[S->start[type] + local / (3 * nstrips)], type);
         const int Y0 = v.by * 8, X0 = v.bx * 8;
+        float *plane = c == 0 ? P.out[0] : (c == 1 ? P.out[1] : P.out[2]);
+        const float *lfc = c == 0 ? P.lf[0] : (c == 1 ? P.lf[1] : P.lf[2]);
+        const ChanCtx kc = make_chan(P, v, c);
 
         if (PASS == 0) {
-            // rows i = 0..N-1 of 32 columns: coalesced 128-byte reads of the three coefficient planes
+            // rows i = 0..N-1 of 32 columns: coalesced 128-byte reads of the coefficient plane(s)
             for (int i = warp; i < N; i += nwarps) {
                 const int lx = strip * 32 + lane;
-                float X = 0.0f, Y = 0.0f, B = 0.0f;
-                if (!(i < v.dsH && lx < v.dsW)) dequant3(P, v, i, lx, X, Y, B);
-                A[(0 * N + i) * BIG_PITCH + lane] = X;
-                A[(1 * N + i) * BIG_PITCH + lane] = Y;
-                A[(2 * N + i) * BIG_PITCH + lane] = B;
+                const float val = (i < v.dsH && lx < v.dsW) ? 0.0f : dequant_ch(P, v, kc, i, lx);
+                A[i * BIG_PITCH + lane] = val;
+                if (N > 32) {
+                    const unsigned f = __ballot_sync(0xffffffffu, val != 0.0f);
+                    if (lane == 0) rowflag[i] = f != 0u;
+                }
             }
             if (strip == 0) {
                 // finalizeLLF for a corner up to 32x32: row pass into scratch, column pass into A (overwrites)
                 const int lw = ilog2_pow2(v.dsW), lh = ilog2_pow2(v.dsH);
                 const float invW = 1.0f / (float)v.dsW, invH = 1.0f / (float)v.dsH;
-                for (int i = tid; i < 3 * v.dsH * v.dsW; i += nt) {
-                    const int c = i / (v.dsH * v.dsW), r = i % (v.dsH * v.dsW);
-                    const int y = r / v.dsW, kx = r % v.dsW;
-                    const float *src = P.lf[c] + (size_t)(v.by + y) * P.wb + v.bx;
+                for (int i = tid; i < v.dsH * v.dsW; i += nt) {
+                    const int y = i / v.dsW, kx = i % v.dsW;
+                    const float *src = lfc + (size_t)(v.by + y) * P.wb + v.bx;
                     float d2;
                     if (kx == 0) {
                         d2 = src[0];
@@ -343,13 +400,12 @@ template <int N, int PASS> __global__ void __launch_bounds__(BIG_THREADS) k1_big
                         d2 = __fmul_rn(src[0], lut[0]);
                         for (int n = 1; n < v.dsW; n++) d2 = __fadd_rn(d2, __fmul_rn(src[n], lut[n]));
                     }
-                    scr[(c * 32 + y) * BIG_PITCH + kx] = __fmul_rn(d2, invW);
+                    scr[y * BIG_PITCH + kx] = __fmul_rn(d2, invW);
                 }
                 __syncthreads();
-                for (int i = tid; i < 3 * v.dsH * v.dsW; i += nt) {
-                    const int c = i / (v.dsH * v.dsW), r = i % (v.dsH * v.dsW);
-                    const int ky = r / v.dsW, kx = r % v.dsW;
-                    const float *col = scr + (c * 32) * BIG_PITCH + kx;
+                for (int i = tid; i < v.dsH * v.dsW; i += nt) {
+                    const int ky = i / v.dsW, kx = i % v.dsW;
+                    const float *col = scr + kx;
                     float d2;
                     if (ky == 0) {
                         d2 = col[0];
@@ -361,90 +417,148 @@ template <int N, int PASS> __global__ void __launch_bounds__(BIG_THREADS) k1_big
                     }
                     d2 = __fmul_rn(d2, invH);
                     const float sc = __fmul_rn(c_llf_scale[ky << (5 - lh)], c_llf_scale[kx << (5 - lw)]);
-                    A[(c * N + ky) * BIG_PITCH + kx] = __fmul_rn(d2, sc);
+                    A[ky * BIG_PITCH + kx] = __fmul_rn(d2, sc);
+                    if (N > 32) rowflag[ky] = 1;      // LLF rows are live
+                }
+            }
+            if (N > 32) {
+                __syncthreads();
+                if (warp == 0) {                                 // compact the live rows n >= 1 (n <= 255: a byte each)
+                    int count = 0;
+                    for (int base = 1; base < N; base += 32) {
+                        const int n = base + lane;
+                        const bool f = n < N && rowflag[n] != 0;
+                        const unsigned mk = __ballot_sync(0xffffffffu, f);
+                        if (f) rowlist[count + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)n;
+                        count += __popc(mk);
+                    }
+                    if (lane == 0) rowcnt[0] = count;
                 }
             }
         } else {
-            // 32 rows x N columns of the intermediate plane, transposed into A[c][x][row]
-            for (int i = tid; i < 3 * 32 * N; i += nt) {
-                const int c = i / (32 * N), r = (i / N) % 32, x = i % N;
-                A[(c * N + x) * BIG_PITCH + r] = P.out[c][(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x];
+            // 32 rows x N columns of the intermediate plane into A[n][row]
+            constexpr int PT = N == 32 ? BIG_PITCH : BIG_PITCH1;
+            for (int i = tid; i < 32 * N; i += nt) {
+                const int r = i / N, x = i % N;
+                A[x * PT + r] = plane[(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x];
             }
         }
         __syncthreads();
 
         if (N == 32) {
-            for (int c = warp; c < 3; c += nwarps) {
+            if (warp == 0) {
                 float vv[32];
 #pragma unroll
-                for (int m = 0; m < 32; m++) vv[m] = A[(c * N + m) * BIG_PITCH + lane];
+                for (int m = 0; m < 32; m++) vv[m] = A[m * BIG_PITCH + lane];
                 RefIDCT<32>::run(vv, CosLut());
                 if (PASS == 0) {
 #pragma unroll
-                    for (int m = 0; m < 32; m++)
-                        P.out[c][(size_t)(Y0 + m) * P.out_pitch + X0 + strip * 32 + lane] = vv[m];
+                    for (int m = 0; m < 32; m++) plane[(size_t)(Y0 + m) * P.out_pitch + X0 + strip * 32 + lane] = vv[m];
                 } else {
 #pragma unroll
-                    for (int m = 0; m < 32; m++) A[(c * N + m) * BIG_PITCH + lane] = vv[m];
+                    for (int m = 0; m < 32; m++) A[m * BIG_PITCH + lane] = vv[m];
                 }
             }
-        } else {
+            if (PASS == 1) {
+                __syncthreads();
+                for (int i = tid; i < 32 * N; i += nt) {
+                    const int r = i / N, x = i % N;
+                    plane[(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x] = A[x * BIG_PITCH + r];
+                }
+            }
+        } else if (PASS == 0) {
             const float *__restrict__ lut = P.cos_big + cos_big_off(N);
-            for (int w = warp; w < 3 * (N / 32); w += nwarps) {
-                const int c = w / (N / 32), k0 = (w % (N / 32)) * 16;
-                const float *src = A + (c * N) * BIG_PITCH + lane;
-                float lo[16], hi[16];
+            for (int w = warp; w < N / 16; w += nwarps) {
+                const int k0 = w * 8;
+                const float *src = A + lane;
+                const unsigned char *lst = rowlist;
+                const int cnt = rowcnt[0];
+                float lo[8], hi[8], la[8], lb[8];
                 const float in0 = src[0];
 #pragma unroll
-                for (int q = 0; q < 16; q++) { lo[q] = in0; hi[q] = in0; }
-#pragma unroll 2
-                for (int n = 1; n < N; n++) {
+                for (int q = 0; q < 8; q++) { lo[q] = in0; hi[q] = in0; }
+                auto step = [&](int n, const float (&l)[8]) {
                     const float s2 = src[n * BIG_PITCH];
-                    if (__ballot_sync(0xffffffffu, s2 != 0.0f) == 0u) continue;
-                    const float4 *lv = reinterpret_cast<const float4 *>(lut + (n - 1) * N + k0);
-                    float l[16];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float4 t4 = __ldg(lv + q);
-                        l[4 * q] = t4.x; l[4 * q + 1] = t4.y; l[4 * q + 2] = t4.z; l[4 * q + 3] = t4.w;
-                    }
                     if (n & 1) {
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
+                        for (int q = 0; q < 8; q++) {
                             const float p = __fmul_rn(s2, l[q]);
                             lo[q] = __fadd_rn(lo[q], p);
                             hi[q] = __fsub_rn(hi[q], p);
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
+                        for (int q = 0; q < 8; q++) {
                             const float p = __fmul_rn(s2, l[q]);
                             lo[q] = __fadd_rn(lo[q], p);
                             hi[q] = __fadd_rn(hi[q], p);
                         }
                     }
+                };
+                int na = cnt > 0 ? lst[0] : 1;
+                if (cnt > 0) ld_lut8(lut + (na - 1) * N + k0, la);
+#pragma unroll 1
+                for (int idx = 0; idx < cnt; idx += 2) {
+                    const int nb = idx + 1 < cnt ? lst[idx + 1] : 1;
+                    if (idx + 1 < cnt) ld_lut8(lut + (nb - 1) * N + k0, lb);     // one live row ahead
+                    step(na, la);
+                    if (idx + 1 >= cnt) break;
+                    na = idx + 2 < cnt ? lst[idx + 2] : 1;
+                    if (idx + 2 < cnt) ld_lut8(lut + (na - 1) * N + k0, la);
+                    step(nb, lb);
                 }
-                if (PASS == 0) {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        P.out[c][(size_t)(Y0 + k0 + q) * P.out_pitch + X0 + strip * 32 + lane] = lo[q];
-                        P.out[c][(size_t)(Y0 + N - 1 - k0 - q) * P.out_pitch + X0 + strip * 32 + lane] = hi[q];
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        T[(c * N + k0 + q) * BIG_PITCH + lane] = lo[q];
-                        T[(c * N + N - 1 - k0 - q) * BIG_PITCH + lane] = hi[q];
-                    }
+                for (int q = 0; q < 8; q++) {
+                    plane[(size_t)(Y0 + k0 + q) * P.out_pitch + X0 + strip * 32 + lane] = lo[q];
+                    plane[(size_t)(Y0 + N - 1 - k0 - q) * P.out_pitch + X0 + strip * 32 + lane] = hi[q];
                 }
             }
-        }
-        if (PASS == 1) {
-            __syncthreads();
-            const float *O = N == 32 ? A : T;
-            for (int i = tid; i < 3 * 32 * N; i += nt) {
-                const int c = i / (32 * N), r = (i / N) % 32, x = i % N;
-                P.out[c][(size_t)(Y0 + strip * 32 + r) * P.out_pitch + X0 + x] = O[(c * N + x) * BIG_PITCH + r];
+        } else {
+            const float *__restrict__ lut = P.cos_big + cos_big_off(N);
+            constexpr int KCH = N / 64;                 // 32-lane chunks of k in [0, N/2)
+            for (int w = warp; w < 2 * KCH; w += nwarps) {
+                const int rg = w / KCH, k = (w % KCH) * 32 + lane;
+                const float *src = A + 16 * rg;
+                float lo[16], hi[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(src + 4 * g);
+                    lo[4 * g] = hi[4 * g] = t4.x; lo[4 * g + 1] = hi[4 * g + 1] = t4.y;
+                    lo[4 * g + 2] = hi[4 * g + 2] = t4.z; lo[4 * g + 3] = hi[4 * g + 3] = t4.w;
+                }
+                // table entries four n ahead (L2 latency ~ 4 iterations of this loop)
+                float lq[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) lq[u] = __ldg(lut + u * N + k);
+#pragma unroll 1
+                for (int n0 = 1; n0 < N; n0 += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int n = n0 + u;
+                        if (n >= N) break;
+                        const float l = lq[u];
+                        if (n + 4 < N) lq[u] = __ldg(lut + (n + 3) * N + k);
+                        const float *sn = src + n * BIG_PITCH1;
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(sn + 4 * g);
+                            const float in4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float p = __fmul_rn(in4[e], l);
+                                lo[4 * g + e] = __fadd_rn(lo[4 * g + e], p);
+                                // n0 is odd, so n is odd exactly when u is even
+                                hi[4 * g + e] = (u & 1) ? __fadd_rn(hi[4 * g + e], p) : __fsub_rn(hi[4 * g + e], p);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    float *o = plane + (size_t)(Y0 + strip * 32 + 16 * rg + r) * P.out_pitch + X0;
+                    o[k] = lo[r];
+                    o[N - 1 - k] = hi[r];
+                }
             }
         }
         __syncthreads();

@@ -5,7 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "k0_lists.cuh"
@@ -36,6 +38,7 @@ struct jxlb200_ctx {
     int device = 0;
     int sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host entry point
     std::string err;
     int64_t launches = 0;
     bool have_weights = false;
@@ -157,12 +160,16 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     CUDA_TRY(ctx, ctx->sched.ensure(sizeof(Sched)));
     CUDA_TRY(ctx, ctx->items.ensure(sizeof(int) * (size_t)wb * hb));
     CUDA_TRY(ctx, ctx->gate.ensure(sizeof(int) * (size_t)tw * th));
+    if (!ctx->flags.p) {
+        CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, ctx->stream));
+    }
     cudaStream_t st = ctx->stream;
     Sched *S = ctx->sched.as<Sched>();
     CUDA_TRY(ctx, cudaMemsetAsync(S, 0, sizeof(Sched), st));
     const int ncells = wb * hb;
     const int g0 = min(ctx->sms * 4, ceil_div(ncells, 256));
-    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, S);
+    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, S, ctx->flags.as<int>() + 2);
     k0_plan<<<1, 32, 0, st>>>(S);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->gate.p, 0x7f, sizeof(int) * (size_t)tw * th, st));
     k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>(), ctx->gate.as<int>(), tw);
@@ -240,7 +247,10 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
     if (K.iters > 0) {
         CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * (rows / 8 + 2)));
         CUDA_TRY(ctx, ctx->lut8.ensure(sizeof(float) * 8));
-        CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+        if (!ctx->flags.p) {
+            CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, st));
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->lut8.p, K.sharp_lut, sizeof(float) * 8, cudaMemcpyHostToDevice, st));
         inv_sigma = ctx->sigma.as<float>() + wb;
         const int br0 = K.has_top ? -1 : 0, br1 = rows / 8 + (K.has_bottom ? 1 : 0);
@@ -334,26 +344,15 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
     return 0;
 }
 
-// device error flags -> status (dct_select out of range, sharpness outside 0..7)
+// device error flags -> status: [0] sharpness outside 0..7, [1] palette scratch, [2] dct_select out of range
 int check_flags(jxlb200_ctx *ctx) {
-    int rc = 0;
-    if (ctx->sched.p) {
-        int e = 0;
-        CUDA_TRY(ctx, cudaMemcpy(&e, (char *)ctx->sched.p + offsetof(Sched, error), sizeof(int), cudaMemcpyDeviceToHost));
-        if (e) {
-            cudaMemset((char *)ctx->sched.p + offsetof(Sched, error), 0, sizeof(int));
-            rc = ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select (HFMetadata.java:45-46)");
-        }
-    }
-    if (ctx->flags.p) {
-        int e = 0;
-        CUDA_TRY(ctx, cudaMemcpy(&e, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (e) {
-            cudaMemset(ctx->flags.p, 0, sizeof(int) * 4);
-            rc = ctx->fail(JXLB200_E_STREAM, "Invalid EPF Sharpness (Frame.java:565-566)");
-        }
-    }
-    return rc;
+    if (!ctx->flags.p) return 0;
+    int e[4] = {0, 0, 0, 0};
+    CUDA_TRY(ctx, cudaMemcpy(e, ctx->flags.p, sizeof(e), cudaMemcpyDeviceToHost));
+    if (!e[0] && !e[2]) return 0;
+    cudaMemset(ctx->flags.p, 0, sizeof(e));
+    if (e[2]) return ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select (HFMetadata.java:45-46)");
+    return ctx->fail(JXLB200_E_STREAM, "Invalid EPF Sharpness (Frame.java:565-566)");
 }
 
 struct HostMaps {   // device copies of the per-block maps, packed into one allocation
@@ -400,6 +399,8 @@ int32_t jxlb200_create(int32_t device, jxlb200_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return JXLB200_E_CUDA; }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { jxlb200_destroy(ctx); return JXLB200_E_CUDA; }
     int rc = upload_constants(ctx);
     if (rc) { fprintf(stderr, "jxlb200_create: %s\n", ctx->err.c_str()); jxlb200_destroy(ctx); return rc; }
     *out = ctx;
@@ -414,6 +415,8 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
                      &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod};
     for (DevBuf *b : all) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }
 
@@ -527,6 +530,12 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
     return check_flags(ctx);
 }
 
+// Whole path on host buffers.  Frames taller than one slab are pipelined by group rows over three streams: while slab i
+// is uploaded (copy engine 1), stage 1 of slab i-1 and stage 2 of slab i-2 run, and slab i-3's pixels go back (copy engine
+// 2) -- PCIe is full duplex, so the call costs about max(upload, download, compute) instead of their sum.  Stage 2 of a
+// slab needs HALO rows of the next slab's stage-1 output, hence the one-slab lag; the planes are contiguous on the
+// device, so "halo rows" are simply the neighbouring slab's rows (jxlb200_slab with has_top / has_bottom).
+#define JXLB200_PIPE_ROWS 512
 int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
@@ -535,19 +544,85 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
     if (rc) return rc;
     if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !sharpness || !out)
         return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    for (int c = 0; c < 3; c++)
+        if (!qcoeff[c] || !lf[c] || !out[c]) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t npx = (size_t)p->width * p->height, nb = npx / 64;
-    void *dq[3], *dlf[3];
-    if ((rc = stage_in_planes(ctx, ctx->in_q, (const void *const *)qcoeff, sizeof(int32_t) * npx, dq))) return rc;
-    if ((rc = stage_in_planes(ctx, ctx->in_lf, (const void *const *)lf, sizeof(float) * nb, dlf))) return rc;
+    const int W = p->width, H = p->height, wb = W >> 3, tw = (W + 63) >> 6;
+    const size_t npx = (size_t)W * H, nb = npx / 64;
+    CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(int32_t) * npx));
+    CUDA_TRY(ctx, ctx->in_lf.ensure(3 * sizeof(float) * nb));
+    CUDA_TRY(ctx, ctx->mid.ensure(3 * sizeof(float) * npx));
+    CUDA_TRY(ctx, ctx->out_planes.ensure(3 * sizeof(float) * npx));
+    int32_t *dq[3]; float *dlf[3], *mid[3], *dout[3];
+    for (int c = 0; c < 3; c++) {
+        dq[c] = ctx->in_q.as<int32_t>() + c * npx;
+        dlf[c] = ctx->in_lf.as<float>() + c * nb;
+        mid[c] = ctx->mid.as<float>() + c * npx;
+        dout[c] = ctx->out_planes.as<float>() + c * npx;
+    }
+    cudaStream_t comp = ctx->stream, up = ctx->h2d_stream, down = ctx->d2h_stream;
     HostMaps M;
-    if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
-    CUDA_TRY(ctx, ctx->out_planes.ensure(sizeof(float) * 3 * npx));
-    float *dout[3] = {ctx->out_planes.as<float>(), ctx->out_planes.as<float>() + npx, ctx->out_planes.as<float>() + 2 * npx};
-    rc = jxlb200_vardct_reconstruct_dev(ctx, p, (const int32_t *const *)dq, (const float *const *)dlf, M.ds, M.bo, M.hf, M.xfy, M.bfy,
-                                        M.sharp, dout);
+    {   // the small per-block maps go first, on the upload stream
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = up;
+        rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M);
+        ctx->stream = keep;
+        if (rc) return rc;
+    }
+    const int nslab = ceil_div(H, JXLB200_PIPE_ROWS);
+    std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);
+    for (int i = 0; i < nslab; i++) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], cudaEventDisableTiming));
+    }
+    auto slab_y0 = [&](int i) { return i * JXLB200_PIPE_ROWS; };
+    auto slab_rows = [&](int i) { return std::min(JXLB200_PIPE_ROWS, H - i * JXLB200_PIPE_ROWS); };
+    rc = 0;
+    for (int i = 0; i <= nslab && !rc; i++) {
+        if (i < nslab) {
+            const int y0 = slab_y0(i), rows = slab_rows(i);
+            for (int c = 0; c < 3 && !rc; c++) {
+                cudaError_t e = cudaMemcpyAsync(dq[c] + (size_t)y0 * W, qcoeff[c] + (size_t)y0 * W, sizeof(int32_t) * (size_t)rows * W, cudaMemcpyHostToDevice, up);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(dlf[c] + (size_t)(y0 / 8) * wb, lf[c] + (size_t)(y0 / 8) * wb, sizeof(float) * (size_t)(rows / 8) * wb, cudaMemcpyHostToDevice, up);
+                if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (upload)", e);
+            }
+            if (rc) break;
+            cudaEventRecord(ev_up[i], up);
+            cudaStreamWaitEvent(comp, ev_up[i], 0);
+            // stage 1 of slab i: a frame of `rows` rows whose planes start at row y0
+            jxlb200_frame_params ps = *p;
+            ps.height = rows;
+            const int32_t *q3[3] = {dq[0] + (size_t)y0 * W, dq[1] + (size_t)y0 * W, dq[2] + (size_t)y0 * W};
+            const float *l3[3] = {dlf[0] + (size_t)(y0 / 8) * wb, dlf[1] + (size_t)(y0 / 8) * wb, dlf[2] + (size_t)(y0 / 8) * wb};
+            float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
+            rc = invert_dev(ctx, &ps, q3, l3, M.ds + (size_t)(y0 / 8) * wb, M.bo + (size_t)(y0 / 8) * wb, M.hf + (size_t)(y0 / 8) * wb,
+                            M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W);
+            if (rc) break;
+        }
+        if (i >= 1) {
+            // stage 2 of slab i-1 (its lower halo rows were written by stage 1 of slab i just above)
+            const int j = i - 1, y0 = slab_y0(j), rows = slab_rows(j);
+            jxlb200_frame_params ps = *p;
+            ps.height = rows;
+            jxlb200_slab sl = {y0, rows, H, j > 0 ? 1 : 0, j < nslab - 1 ? 1 : 0};
+            const float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
+            float *o3[3] = {dout[0] + (size_t)y0 * W, dout[1] + (size_t)y0 * W, dout[2] + (size_t)y0 * W};
+            rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(y0 / 8) * wb, M.sharp + (size_t)(y0 / 8) * wb, o3);
+            if (rc) break;
+            cudaEventRecord(ev_k2[j], comp);
+            cudaStreamWaitEvent(down, ev_k2[j], 0);
+            for (int c = 0; c < 3 && !rc; c++) {
+                cudaError_t e = cudaMemcpyAsync(out[c] + (size_t)y0 * W, o3[c], sizeof(float) * (size_t)rows * W, cudaMemcpyDeviceToHost, down);
+                if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (download)", e);
+            }
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(down);
+    for (int i = 0; i < nslab; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k2[i]); }
     if (rc) return rc;
-    return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return ctx->fail(JXLB200_E_CUDA, "stream synchronize", e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+    return check_flags(ctx);
 }
 
 int32_t jxlb200_vardct_invert(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
@@ -653,7 +728,10 @@ int32_t jxlb200_modular_palette_dev(jxlb200_ctx *ctx, const int32_t *idx, const 
     if (d_pred == 6) return ctx->fail(JXLB200_E_UNSUPPORTED, "palette delta with the weighted predictor (reference dereferences null pred[][])");
     if (h == 0 || w == 0) return 0;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+    if (!ctx->flags.p) {
+        CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, ctx->stream));
+    }
     int *any = ctx->flags.as<int>() + 1;
     PalArgs A{idx, palette, h, w, num_c, nb_colors, nb_deltas, d_pred, bit_depth};
     const long long n = (long long)h * w;

@@ -17,7 +17,7 @@ static const int h_big_types[2][N_BIGC][3] = {
     {{19, -1, -1}, {18, 20, 22}, {21, 23, 25}, {24, 26, -1}},
 };
 
-__global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int ncells, Sched *s) {
+__global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int ncells, Sched *s, int *__restrict__ err) {
     __shared__ int h[27];
     __shared__ int bad;
     if (threadIdx.x < 27) h[threadIdx.x] = 0;
@@ -30,7 +30,7 @@ __global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restri
     }
     __syncthreads();
     if (threadIdx.x < 27 && h[threadIdx.x]) atomicAdd(&s->cnt[threadIdx.x], h[threadIdx.x]);
-    if (threadIdx.x == 0 && bad) s->error = 1;
+    if (threadIdx.x == 0 && bad) *err = 1;   // sticky across the slabs of a pipelined frame (Sched is reset per slab)
 }
 
 __global__ void k0_plan(Sched *s) {

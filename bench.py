@@ -250,10 +250,18 @@ def run_ours(args):
                                           d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), xyb, W))
         t2 = timed(lambda: rec.restore_dev(p, None, xyb, W, d["hf_mul"].data_ptr(), d["sharpness"].data_ptr(), out))
         peak, which = peaks()
-        dom = "stage 2 (Gaborish+EPF+colour)" if t2 >= t1 else "stage 1 (dequant+CfL+LLF+IDCT)"
+        dom = "k2_exact (fused Gaborish+EPF+colour)" if t2 >= t1 else "stage 1 (k1_small/medium/big: dequant+CfL+LLF+IDCT)"
         bpp = BYTES_PER_PX_K2 if t2 >= t1 else BYTES_PER_PX
         ach = bpp * W * H / (max(t1, t2) / 1e3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:   # dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if t2 >= t1 and iters == 3 and (W, H) == (7680, 4320):
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": dom, "peak_source": which, "algorithmic_bytes_per_px": bpp,
                 "stage_ms": {"stage1_dequant_idct": t1, "stage2_gab_epf_color": t2},
                 "pipeline_frac": BYTES_PER_PX * W * H / ((t1 + t2) / 1e3) / 1e9 / peak}

@@ -39,6 +39,9 @@ struct jxlb200_ctx {
     int sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the pipelined host entry point
+    // stage 1 fans out over six streams: its kernels touch disjoint varblocks and each is latency-bound on its own
+    cudaStream_t k1_stream[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_p0[4] = {nullptr, nullptr, nullptr, nullptr}, ev_done[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
     bool have_weights = false;
@@ -144,10 +147,10 @@ int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
     return 0;
 }
 
-template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls) {
+template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls, cudaStream_t st) {
     using Cfg = BigCfg<N, PASS>;
     const int per_sm = max(1, min(min(2048 / Cfg::kThreads, 16), (227 * 1024) / (Cfg::kBytes + 1024)));
-    k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, ctx->stream>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
+    k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, st>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
     ctx->launches++;
 }
 
@@ -192,11 +195,24 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     P.qbn = p->quant_bias_numerator;
     P.base_x = p->base_corr_x; P.base_b = p->base_corr_b; P.color_factor = (float)p->color_factor;
 
-    k1_small<<<min(ctx->sms * 8, ceil_div(ncells, SMALL_BATCH)), 128, 0, st>>>(P, S, ctx->items.as<int>());
-    k1_medium<<<min(ctx->sms * 4, ceil_div(ncells, 2)), 256, 0, st>>>(P, S, ctx->items.as<int>());
+    // fan out: small | medium | four line-length classes of the big kernels (pass 0, then pass 1 once every pass 0 is done:
+    // a varblock's row pass runs in the class of its width, its column pass in the class of its height)
+    cudaStream_t *ks = ctx->k1_stream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (int i = 0; i < 6; i++) CUDA_TRY(ctx, cudaStreamWaitEvent(ks[i], ctx->ev_fork, 0));
+    k1_small<<<min(ctx->sms * 8, ceil_div(ncells, SMALL_BATCH)), 128, 0, ks[0]>>>(P, S, ctx->items.as<int>());
+    k1_medium<<<min(ctx->sms * 4, ceil_div(ncells, 2)), 256, 0, ks[1]>>>(P, S, ctx->items.as<int>());
     ctx->launches += 2;
-    launch_big<32, 0>(ctx, P, 0); launch_big<64, 0>(ctx, P, 1); launch_big<128, 0>(ctx, P, 2); launch_big<256, 0>(ctx, P, 3);
-    launch_big<32, 1>(ctx, P, 0); launch_big<64, 1>(ctx, P, 1); launch_big<128, 1>(ctx, P, 2); launch_big<256, 1>(ctx, P, 3);
+    launch_big<256, 0>(ctx, P, 3, ks[5]); launch_big<128, 0>(ctx, P, 2, ks[4]); launch_big<64, 0>(ctx, P, 1, ks[3]); launch_big<32, 0>(ctx, P, 0, ks[2]);
+    for (int k = 0; k < 4; k++) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_p0[k], ks[2 + k]));
+    for (int k = 0; k < 4; k++)
+        for (int j = 0; j < 4; j++)
+            if (j != k) CUDA_TRY(ctx, cudaStreamWaitEvent(ks[2 + k], ctx->ev_p0[j], 0));
+    launch_big<128, 1>(ctx, P, 2, ks[4]); launch_big<256, 1>(ctx, P, 3, ks[5]); launch_big<64, 1>(ctx, P, 1, ks[3]); launch_big<32, 1>(ctx, P, 0, ks[2]);
+    for (int i = 0; i < 6; i++) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[i], ks[i]));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_done[i], 0));
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
@@ -401,6 +417,12 @@ int32_t jxlb200_create(int32_t device, jxlb200_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { jxlb200_destroy(ctx); return JXLB200_E_CUDA; }
+    bool okst = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 6 && okst; i++)
+        okst = cudaStreamCreateWithFlags(&ctx->k1_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && okst; i++) okst = cudaEventCreateWithFlags(&ctx->ev_p0[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!okst) { jxlb200_destroy(ctx); return JXLB200_E_CUDA; }
     int rc = upload_constants(ctx);
     if (rc) { fprintf(stderr, "jxlb200_create: %s\n", ctx->err.c_str()); jxlb200_destroy(ctx); return rc; }
     *out = ctx;
@@ -416,6 +438,9 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     for (DevBuf *b : all) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    for (int i = 0; i < 6; i++) { if (ctx->k1_stream[i]) cudaStreamDestroy(ctx->k1_stream[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    for (int i = 0; i < 4; i++) if (ctx->ev_p0[i]) cudaEventDestroy(ctx->ev_p0[i]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }

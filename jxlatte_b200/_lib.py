@@ -9,7 +9,7 @@ import os
 from .params import FrameParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libjxlb200.so")
+SO_PATH = os.environ.get("JXLB200_LIB") or os.path.join(_HERE, "libjxlb200.so")   # override: kernel-variant experiments
 
 OK, E_ARG, E_STREAM, E_UNSUPPORTED, E_CUDA = 0, -1, -2, -3, -4
 QM_FLOATS = 3 * 131584

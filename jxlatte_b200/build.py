@@ -5,13 +5,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libjxlb200.so")
+SO = os.environ.get("JXLB_SO") or os.path.join(HERE, "libjxlb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++",
     "-Xptxas", "-v" if os.environ.get("JXLB_PTXAS_V") else "-O3",
-]
+] + os.environ.get("JXLB_EXTRA_FLAGS", "").split()
 
 
 def sources():

@@ -12,6 +12,7 @@ patches, the other blend modes, LF frames, chroma subsampling -- raises NotImple
 `engine` is the reconstruction back end.  The default is the CUDA library (jxlatte_b200.host.Reconstructor); there is no
 CPU fallback in this module -- the CPU tests inject the oracle explicitly (tests/test_frontend.py).
 """
+import ctypes as C
 import struct
 import zlib
 
@@ -204,7 +205,7 @@ class JXLDecoder:
                 if q["mode"] == 7:
                     raw = np.ascontiguousarray(parsed.array(k, "qraw", 3 * i + c), np.float32)
                     keep.append(raw)
-                    prm[i].raw[c] = raw.ctypes.data
+                    prm[i].raw[c] = raw.ctypes.data_as(C.POINTER(C.c_float))
         out = self.engine.qm_generate(prm)
         del keep
         return out

@@ -1,0 +1,116 @@
+"""C++ front end (libjxlfront.so) + decoder glue on real .jxl files (tests/golden/samples, copied sample INPUTS of the
+reference).  The reference ships no decoded outputs and no JVM exists here, so what pins the front end is (a) every ANS
+stream of every file ending in its mandatory final state, (b) the decoded pictures (checked by eye when the fixtures were
+made, pinned here by hash of the oracle's 8-bit output), (c) the GPU decode being bit-identical to the oracle's decode."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from jxlatte_b200 import frontend
+from jxlatte_b200.decoder import JXLDecoder, JXLImage
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+S = os.path.join(G, "samples")
+PINS = json.load(open(os.path.join(G, "frontend_pins.json")))
+
+
+def _parse(name, flags=0):
+    return frontend.parse_file(os.path.join(S, name + ".jxl"), flags)
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_abi_symbols():
+    L = frontend.lib()
+    for sym in ("jxlf_decode", "jxlf_free", "jxlf_error", "jxlf_describe", "jxlf_array"):
+        assert hasattr(L, sym)
+    hdr = open(os.path.join(os.path.dirname(G), "..", "include", "jxlfront.h")).read()
+    for sym in ("jxlf_decode", "jxlf_free", "jxlf_error", "jxlf_describe", "jxlf_array"):
+        assert sym + "(" in hdr
+
+
+@pytest.mark.parametrize("name", ["lenna", "bbb", "white", "bench", "quilt", "art"])
+def test_headers_and_state(name):
+    p = _parse(name)
+    pin = PINS[name]
+    i = p.info
+    assert (i["width"], i["height"], i["xyb_encoded"], i["orientation"]) == tuple(pin["image"])
+    f = p.frames[0]
+    assert [f["encoding"], f["width"], f["height"], f["gab"], f["epf_iters"], f["num_groups"]] == pin["frame"]
+    if f["encoding"] == 0:
+        st = p.vardct_state(0)
+        got = {k: _digest(st[k]) for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
+        assert got == pin["state"]
+        # structural invariants of the varblock partition
+        ds, bo = st["dct_select"], st["block_origin"]
+        from jxlatte_b200.params import TRANSFORM_TYPES
+        area = sum((TRANSFORM_TYPES[t][2] // 8) * (TRANSFORM_TYPES[t][3] // 8) for t in ds[bo == 1])
+        assert area == ds.size
+        assert st["hf_mul"].min() >= 1 and 0 <= st["sharpness"].min() and st["sharpness"].max() <= 7
+    else:
+        ch = p.modular_channels(0)
+        assert [_digest(c) for c in ch] == pin["modular"]
+    p.close()
+
+
+def test_truncated_and_garbage_inputs():
+    data = open(os.path.join(S, "lenna.jxl"), "rb").read()
+    with pytest.raises(frontend.InvalidBitstreamError):
+        frontend.parse(data[:20000])
+    with pytest.raises(frontend.InvalidBitstreamError):
+        frontend.parse(b"not a jxl file at all")
+    bad = bytearray(data)
+    bad[5000] ^= 0x55                      # a flipped bit inside an ANS stream must trip a final-state or range check
+    p = frontend.parse(bytes(bad), strict=False)
+    assert p.status in (-2, 0)
+    if p.status == 0:
+        assert p.vardct_state(0)["qcoeff"].shape == (3, 512, 512)
+
+
+def test_host_transforms_flag_matches_glue():
+    """The frame-level modular transforms undone by the front end itself (test flag) and by the decoder glue with the
+    oracle's transforms agree: two independent implementations of ModularStream.applyTransforms on real data."""
+    from oracle_engine import OracleEngine
+    for name in ("quilt", "art"):
+        a = _parse(name, frontend.FLAG_HOST_TRANSFORMS)
+        b = _parse(name)
+        f = b.frames[0]
+        tr = [dict(tr=t["tr"], begin_c=t["begin_c"], rct_type=t["rct_type"], num_c=t["num_c"], nb_colors=t["nb_colors"],
+                   nb_deltas=t["nb_deltas"], d_pred=t["d_pred"], sp=[(bool(s[0]), bool(s[1]), s[2], s[3]) for s in t["sp"]])
+              for t in f["modular"]["transforms"]]
+        want = OracleEngine().modular(b.modular_channels(0), tr, b.info["bits_per_sample"])
+        got = a.modular_channels(0)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("name", ["lenna", "white", "quilt"])
+def test_decode_with_oracle_engine(name):
+    from oracle_engine import OracleEngine
+    img = JXLDecoder(os.path.join(S, name + ".jxl"), engine=OracleEngine()).decode()
+    assert isinstance(img, JXLImage)
+    assert _digest(img.to_int(8)) == PINS[name]["png8"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lenna", "bbb", "white", "bench", "quilt", "art"])
+def test_gpu_decode_matches_oracle_decode(name):
+    """BASELINE configs[1] (+ the modular art files): the CUDA path and the oracle decode the same real file to the same
+    bits -- planes equal, hence 8- and 16-bit PNG samples equal."""
+    from oracle_engine import OracleEngine
+    path = os.path.join(S, name + ".jxl")
+    want = JXLDecoder(path, engine=OracleEngine()).decode()
+    dec = JXLDecoder(path)
+    got = dec.decode()
+    dec.close()
+    assert got.planes.shape == want.planes.shape
+    assert np.array_equal(got.planes, want.planes)
+    assert np.array_equal(got.to_int(16), want.to_int(16))
+    if name in PINS and "png8" in PINS[name]:
+        assert _digest(got.to_int(8)) == PINS[name]["png8"]

@@ -217,8 +217,6 @@ class JXLDecoder:
             raise NotImplementedError("noise / patches / splines / LF frames (flags=%d): SURVEY.md 8f-3/4" % f["flags"])
         if f["upsampling"] != 1 or any(u != 1 for u in f["ec_upsampling"]):
             raise NotImplementedError("upsampling: SURVEY.md 8f-4")
-        if any(f["shift_x"]) or any(f["shift_y"]):
-            raise NotImplementedError("chroma-subsampled VarDCT: SURVEY.md 8f-2")
         h, w = f["height"], f["width"]
         ncol = 3 if (info["xyb_encoded"] or f["encoding"] == ENC_VARDCT) else info["color_channels"]
         planes = []

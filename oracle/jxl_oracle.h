@@ -91,6 +91,7 @@ int32_t orc_epf(const orc_frame_params *p, float *const buf[3], const int32_t *h
 void orc_color(const orc_frame_params *p, float *const buf[3], int32_t nthreads);
 
 /* Whole path: invert -> gab -> epf -> color.  out[3] receives the final planes. */
+void orc_invert_subsampling(const orc_frame_params *p, const float *const in[3], float *const out[3]);
 int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,

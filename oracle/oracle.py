@@ -115,8 +115,9 @@ def vardct_invert(p, st, nthreads=1, want_dequant=False):
     H, W = p.height, p.width
     q = [_c(st["qcoeff"][c], np.int32) for c in range(3)]
     lf = [_c(st["lf"][c], np.float32) for c in range(3)]
-    out = [np.zeros((H, W), np.float32) for _ in range(3)]
-    dq = [np.zeros((H, W), np.float32) for _ in range(3)] if want_dequant else None
+    dims = [(H >> p.shift_y[c], W >> p.shift_x[c]) for c in range(3)]      # chroma-subsampled channels are smaller
+    out = [np.zeros(dims[c], np.float32) for c in range(3)]
+    dq = [np.zeros(dims[c], np.float32) for c in range(3)] if want_dequant else None
     ds, bo = _c(st["dct_select"], np.uint8), _c(st["block_origin"], np.uint8)
     hm = _c(st["hf_mul"], np.int32)
     xf, bf = _c(st["x_from_y"], np.int32), _c(st["b_from_y"], np.int32)
@@ -127,7 +128,19 @@ def vardct_invert(p, st, nthreads=1, want_dequant=False):
                              _planes(out, C.c_float), _planes(dq, C.c_float) if dq else None, int(nthreads))
     if rc:
         raise RuntimeError("orc_vardct_invert rc=%d" % rc)
+    if len(set(dims)) > 1:
+        return (out, dq) if want_dequant else out
     return (np.stack(out), np.stack(dq)) if want_dequant else np.stack(out)
+
+
+def invert_subsampling(p, planes):
+    """Frame.invertSubsampling: per-channel (H >> sy) x (W >> sx) planes -> three H x W planes."""
+    L = lib()
+    p = as_params(p)
+    inp = [_c(planes[c], np.float32) for c in range(3)]
+    out = [np.zeros((p.height, p.width), np.float32) for _ in range(3)]
+    L.orc_invert_subsampling(C.byref(p), _planes(inp, C.c_float), _planes(out, C.c_float))
+    return np.stack(out)
 
 
 def gab(p, planes, nthreads=1):

@@ -809,7 +809,13 @@ static int process_group(const orc_frame_params *p, int gy, int gx,
 
     int subsampled = 0;
     for (int c = 0; c < 3; c++) if (p->shift_x[c] != 0 || p->shift_y[c] != 0) subsampled = 1;
-    if (subsampled) return -3; /* chroma subsampling: SURVEY 8(f2), not in this build */
+    /* chroma subsampling (jpegUpsamplingY/X): channel c lives in a (H >> sy) x (W >> sx) plane; a varblock takes part in
+     * channel c only when its block position is a multiple of the subsampling factor, and then sits at the shifted
+     * position with the SAME TransformType (HFCoefficients.java:290-303, PassGroup.java:217-226). */
+    int Wc[3], wbc[3];
+    for (int c = 0; c < 3; c++) { Wc[c] = W >> p->shift_x[c]; wbc[c] = wb >> p->shift_x[c]; }
+#define SUB_SKIP(pos, c) ((((pos).y >> p->shift_y[c]) << p->shift_y[c]) != (pos).y || (((pos).x >> p->shift_x[c]) << p->shift_x[c]) != (pos).x)
+#define SUB_ORG(pos, c) ((size_t)(((pos).y >> p->shift_y[c]) << 3) * Wc[c] + (((pos).x >> p->shift_x[c]) << 3))
 
     /* ---- dequantizeHFCoefficients :267-319 ---- */
     float globalScale = 65536.0f / p->global_scale;
@@ -829,13 +835,15 @@ static int process_group(const orc_frame_params *p, int gy, int gx,
         const int mw = tt_matrix_w(tt);
         const int dsH = tt->pixelH >> 3, dsW = tt->pixelW >> 3;
         for (int c = 0; c < 3; c++) {
+            if (SUB_SKIP(pos, c)) continue; /* subsampled block */
             const float *w3 = qm_weights + qm_offsets[tt->parameterIndex * 3 + c];
             float sfc = scaleFactor[c] / hf_mul[pos.y * wb + pos.x];
             const float *qbc = qbclut[c];
+            const size_t org = SUB_ORG(pos, c);
             for (int y = 0; y < tt->pixelH; y++) {
                 for (int x = 0; x < tt->pixelW; x++) {
                     if (y < dsH && x < dsW) continue;
-                    size_t idx = (size_t)((pos.y << 3) + y) * W + (pos.x << 3) + x;
+                    size_t idx = org + (size_t)y * Wc[c] + x;
                     int coeff = qcoeff[c][idx];
                     float quant = (coeff > -2 && coeff < 2) ? qbc[coeff + 1] : coeff - p->quant_bias_numerator / coeff;
                     int wy = flip ? x : y;
@@ -846,8 +854,9 @@ static int process_group(const orc_frame_params *p, int gy, int gx,
         }
     }
 
-    /* ---- chromaFromLuma :146-192 (xFactors/bFactors are fresh zero arrays per call, like the Java) ---- */
-    {
+    /* ---- chromaFromLuma :146-192 (xFactors/bFactors are fresh zero arrays per call, like the Java);
+     * skipped entirely when any channel is subsampled (:149-151) ---- */
+    if (!subsampled) {
         const int th = (H + 63) >> 6;
         memset(xFactors, 0, sizeof(float) * (size_t)th * tw);
         memset(bFactors, 0, sizeof(float) * (size_t)th * tw);
@@ -895,12 +904,13 @@ static int process_group(const orc_frame_params *p, int gy, int gx,
             const tt_t *tt = &TT[type];
             const int dsH = tt->pixelH >> 3, dsW = tt->pixelW >> 3;
             for (int c = 0; c < 3; c++) {
-                const float *dqlf = lf[c] + (size_t)pos.y * wb + pos.x;
-                float *d = dq[c] + (size_t)(pos.y << 3) * W + (pos.x << 3);
-                forward_dct_2d(dqlf, wb, d, W, dsH, dsW, s0, s1, 32);
+                if (SUB_SKIP(pos, c)) continue;
+                const float *dqlf = lf[c] + (size_t)(pos.y >> p->shift_y[c]) * wbc[c] + (pos.x >> p->shift_x[c]);
+                float *d = dq[c] + SUB_ORG(pos, c);
+                forward_dct_2d(dqlf, wbc[c], d, Wc[c], dsH, dsW, s0, s1, 32);
                 for (int y = 0; y < dsH; y++)
                     for (int x = 0; x < dsW; x++)
-                        d[(size_t)y * W + x] *= orc_llf_scale(type, y, x);
+                        d[(size_t)y * Wc[c] + x] *= orc_llf_scale(type, y, x);
             }
         }
     }
@@ -910,11 +920,14 @@ static int process_group(const orc_frame_params *p, int gy, int gx,
         pt_t pos = blocks[i];
         int type = dct_select[pos.y * wb + pos.x];
         for (int c = 0; c < 3; c++) {
-            size_t o = (size_t)(pos.y << 3) * W + (pos.x << 3);
-            int r = invert_varblock(dq[c] + o, W, out[c] + o, W, type, scratch);
+            if (SUB_SKIP(pos, c)) continue;
+            size_t o = SUB_ORG(pos, c);
+            int r = invert_varblock(dq[c] + o, Wc[c], out[c] + o, Wc[c], type, scratch);
             if (r) return r;
         }
     }
+#undef SUB_SKIP
+#undef SUB_ORG
     return 0;
 }
 
@@ -930,9 +943,11 @@ int32_t orc_vardct_invert(const orc_frame_params *p,
     const int groupRows = (H + 255) >> 8, groupCols = (W + 255) >> 8; /* Frame.java:127-129, groupDim 256 */
     float *dq[3];
     int own = dequant_out == NULL || dequant_out[0] == NULL;
+    size_t plane_n[3];
+    for (int c = 0; c < 3; c++) plane_n[c] = (size_t)(W >> p->shift_x[c]) * (H >> p->shift_y[c]);
     for (int c = 0; c < 3; c++)
-        dq[c] = own ? (float *)calloc((size_t)W * H, sizeof(float)) : dequant_out[c];
-    if (!own) for (int c = 0; c < 3; c++) memset(dq[c], 0, sizeof(float) * (size_t)W * H);
+        dq[c] = own ? (float *)calloc(plane_n[c], sizeof(float)) : dequant_out[c];
+    if (!own) for (int c = 0; c < 3; c++) memset(dq[c], 0, sizeof(float) * plane_n[c]);
     int rc = 0;
     const int tw = (W + 63) >> 6, th = (H + 63) >> 6;
     if (nthreads < 1) nthreads = 1;
@@ -1158,6 +1173,51 @@ void orc_color(const orc_frame_params *p, float *const buf[3], int32_t nthreads)
     }
 }
 
+/* Frame.invertSubsampling (J/frame/Frame.java:681-723): per channel, xShift horizontal doublings then yShift vertical
+ * doublings; out = 0.75f * centre + 0.25f * neighbour, neighbour clamped at the plane edge.
+ * in[c]: (H >> sy) x (W >> sx); out[c]: H x W (may be the same pointer when the channel is not subsampled). */
+void orc_invert_subsampling(const orc_frame_params *p, const float *const in[3], float *const out[3]) {
+    const int W = p->width, H = p->height;
+    for (int c = 0; c < 3; c++) {
+        int w = W >> p->shift_x[c], h = H >> p->shift_y[c];
+        float *cur = (float *)malloc(sizeof(float) * (size_t)w * h);
+        memcpy(cur, in[c], sizeof(float) * (size_t)w * h);
+        int xShift = p->shift_x[c];
+        while (xShift-- > 0) {
+            float *nw = (float *)malloc(sizeof(float) * (size_t)w * 2 * h);
+            for (int y = 0; y < h; y++) {
+                const float *oldRow = cur + (size_t)y * w;
+                float *newRow = nw + (size_t)y * w * 2;
+                for (int x = 0; x < w; x++) {
+                    float b75 = 0.75f * oldRow[x];
+                    newRow[2 * x] = b75 + 0.25f * oldRow[x == 0 ? 0 : x - 1];
+                    newRow[2 * x + 1] = b75 + 0.25f * oldRow[x + 1 == w ? w - 1 : x + 1];
+                }
+            }
+            free(cur); cur = nw; w *= 2;
+        }
+        int yShift = p->shift_y[c];
+        while (yShift-- > 0) {
+            float *nw = (float *)malloc(sizeof(float) * (size_t)w * h * 2);
+            for (int y = 0; y < h; y++) {
+                const float *oldRow = cur + (size_t)y * w;
+                const float *oldRowPrev = cur + (size_t)(y == 0 ? 0 : y - 1) * w;
+                const float *oldRowNext = cur + (size_t)(y + 1 == h ? h - 1 : y + 1) * w;
+                float *firstNewRow = nw + (size_t)(2 * y) * w;
+                float *secondNewRow = nw + (size_t)(2 * y + 1) * w;
+                for (int x = 0; x < w; x++) {
+                    float b75 = 0.75f * oldRow[x];
+                    firstNewRow[x] = b75 + 0.25f * oldRowPrev[x];
+                    secondNewRow[x] = b75 + 0.25f * oldRowNext[x];
+                }
+            }
+            free(cur); cur = nw; h *= 2;
+        }
+        memcpy(out[c], cur, sizeof(float) * (size_t)W * H);
+        free(cur);
+    }
+}
+
 /* Frame.decodeFrame tail :457-461 + JXLCodestreamDecoder.decode :637 */
 int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
@@ -1165,9 +1225,26 @@ int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness,
     const float *qm_weights, const int32_t *qm_offsets,
     float *const out[3], int32_t nthreads) {
-    int rc = orc_vardct_invert(p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y,
+    int subsampled = 0;
+    for (int c = 0; c < 3; c++) if (p->shift_x[c] != 0 || p->shift_y[c] != 0) subsampled = 1;
+    int rc;
+    if (!subsampled) {
+        rc = orc_vardct_invert(p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y,
                                qm_weights, qm_offsets, out, NULL, nthreads);
-    if (rc) return rc;
+        if (rc) return rc;
+    } else {
+        float *sub[3];
+        for (int c = 0; c < 3; c++)
+            sub[c] = (float *)calloc((size_t)(p->width >> p->shift_x[c]) * (p->height >> p->shift_y[c]), sizeof(float));
+        rc = orc_vardct_invert(p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y,
+                               qm_weights, qm_offsets, sub, NULL, nthreads);
+        if (!rc) {
+            const float *in[3] = {sub[0], sub[1], sub[2]};
+            orc_invert_subsampling(p, in, out);
+        }
+        for (int c = 0; c < 3; c++) free(sub[c]);
+        if (rc) return rc;
+    }
     if (p->gab) {
         const size_t n = (size_t)p->width * p->height;
         float *tmp[3];

@@ -16,6 +16,7 @@
 #include "k2_fused.cuh"
 #include "k2_exact.cuh"
 #include "k3_modular.cuh"
+#include "k6_subsample.cuh"
 #include "qm_tables.cuh"
 
 // grow-only device allocation
@@ -51,6 +52,7 @@ struct jxlb200_ctx {
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
     DevTables tab;
 
     int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -139,9 +141,12 @@ int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
     if (p->width <= 0 || p->height <= 0 || (p->width & 7) || (p->height & 7))
         return ctx->fail(JXLB200_E_ARG, "padded frame size must be positive multiples of 8");
     if (p->width > 65535 * 8 || p->height > 65535 * 8) return ctx->fail(JXLB200_E_ARG, "frame too large");
-    for (int c = 0; c < 3; c++)
-        if (p->shift_x[c] || p->shift_y[c])
-            return ctx->fail(JXLB200_E_UNSUPPORTED, "chroma subsampling (jpegUpsampling != 0) is not implemented in this build");
+    for (int c = 0; c < 3; c++) {
+        if (p->shift_x[c] < 0 || p->shift_x[c] > 1 || p->shift_y[c] < 0 || p->shift_y[c] > 1)
+            return ctx->fail(JXLB200_E_ARG, "jpegUpsampling shift outside 0..1 (FrameHeader.java:98-117)");
+        if ((p->shift_x[c] && (p->width & 15)) || (p->shift_y[c] && (p->height & 15)))
+            return ctx->fail(JXLB200_E_ARG, "subsampled frame size must be padded to 16 (Frame.getPaddedFrameSize)");
+    }
     if (p->epf_iters < 0 || p->epf_iters > 3) return ctx->fail(JXLB200_E_ARG, "epf_iters outside 0..3");
     if (p->global_scale == 0) return ctx->fail(JXLB200_E_ARG, "global_scale is 0");
     return 0;
@@ -154,10 +159,17 @@ template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, 
     ctx->launches++;
 }
 
+bool is_subsampled(const jxlb200_frame_params *p) {
+    for (int c = 0; c < 3; c++)
+        if (p->shift_x[c] || p->shift_y[c]) return true;
+    return false;
+}
+
 // stage 1 on device pointers
 int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *const q[3], const float *const lf[3],
                const uint8_t *ds, const uint8_t *bo, const int32_t *hf_mul, const int32_t *xfy, const int32_t *bfy,
                float *const out[3], long long pitch) {
+    if (is_subsampled(p)) return ctx->fail(JXLB200_E_UNSUPPORTED, "stage 1 alone does not take chroma-subsampled frames: use jxlb200_vardct_reconstruct[_dev]");
     if (!ctx->have_weights) return ctx->fail(JXLB200_E_ARG, "jxlb200_set_qm_weights has not been called");
     const int W = p->width, H = p->height, wb = W >> 3, hb = H >> 3, tw = (W + 63) >> 6, th = (H + 63) >> 6;
     CUDA_TRY(ctx, ctx->sched.ensure(sizeof(Sched)));
@@ -212,6 +224,62 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     for (int i = 0; i < 6; i++) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[i], ks[i]));
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_done[i], 0));
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Stage 1 of a chroma-subsampled frame (k6_subsample.cuh).  q[c], lf[c]: channel c's own (H >> sy) x (W >> sx) planes;
+// out[c]: full-size planes.  Stage 1 runs once per channel on that channel's plane with strided block maps; the kernel's
+// three channel slots all read the same plane and only slot c (which carries channel c's weights and scale) is kept.
+// Chroma-from-luma is off for such frames (HFCoefficients.java:149-151): base correlations and factor maps are zero.
+int invert_subsampled_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *const q[3], const float *const lf[3],
+                          const uint8_t *ds, const int32_t *hf_mul, float *const out[3]) {
+    const int W = p->width, H = p->height, wb = W >> 3, hb = H >> 3;
+    const size_t npx = (size_t)W * H, nb = (size_t)wb * hb, nt = (size_t)((W + 63) >> 6) * ((H + 63) >> 6);
+    CUDA_TRY(ctx, ctx->sub.ensure(sizeof(float) * 4 * npx));
+    const size_t nb4 = (nb + 3) & ~(size_t)3;
+    CUDA_TRY(ctx, ctx->sub_maps.ensure(2 * nb4 + sizeof(int32_t) * (nb + 2 * nt)));
+    if (!ctx->flags.p) {
+        CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, ctx->stream));
+    }
+    cudaStream_t st = ctx->stream;
+    char *mb = (char *)ctx->sub_maps.p;
+    uint8_t *ds_c = (uint8_t *)mb, *bo_c = (uint8_t *)(mb + nb4);
+    int32_t *hf_c = (int32_t *)(mb + 2 * nb4), *zero_tiles = hf_c + nb;
+    CUDA_TRY(ctx, cudaMemsetAsync(zero_tiles, 0, sizeof(int32_t) * 2 * nt, st));
+    float *plane[4];
+    for (int i = 0; i < 4; i++) plane[i] = ctx->sub.as<float>() + i * npx;
+    for (int c = 0; c < 3; c++) {
+        const int sy = p->shift_y[c], sx = p->shift_x[c];
+        const int Hc = H >> sy, Wc = W >> sx, hbc = hb >> sy, wbc = wb >> sx;
+        k6_submap<<<min(ctx->sms * 4, ceil_div(hbc * wbc, 256)), 256, 0, st>>>(ds, hf_mul, wb, hbc, wbc, sy, sx, ds_c, bo_c, hf_c, ctx->flags.as<int>() + 3);
+        ctx->launches++;
+        jxlb200_frame_params pc = *p;
+        pc.width = Wc; pc.height = Hc;
+        pc.base_corr_x = 0.0f; pc.base_corr_b = 0.0f;
+        for (int k = 0; k < 3; k++) pc.shift_x[k] = pc.shift_y[k] = 0;
+        const int32_t *q3[3] = {q[c], q[c], q[c]};
+        const float *l3[3] = {lf[c], lf[c], lf[c]};
+        float *keep = (sy | sx) ? plane[0] : out[c];          // slot c's plane; the other two slots are scratch
+        float *o3[3];
+        for (int k = 0, sc = 1; k < 3; k++) o3[k] = k == c ? keep : plane[sc++];
+        int rc = invert_dev(ctx, &pc, q3, l3, ds_c, bo_c, hf_c, zero_tiles, zero_tiles + nt, o3, Wc);
+        if (rc) return rc;
+        // Frame.invertSubsampling: horizontal doublings first, then vertical
+        const float *cur = keep;
+        int h = Hc, w = Wc;
+        if (sx) {
+            float *dst = sy ? plane[3] : out[c];
+            k6_upsample_h<<<min(ctx->sms * 8, ceil_div(h * w, 256)), 256, 0, st>>>(cur, h, w, dst);
+            ctx->launches++;
+            cur = dst; w *= 2;
+        }
+        if (sy) {
+            k6_upsample_v<<<min(ctx->sms * 8, ceil_div(h * w, 256)), 256, 0, st>>>(cur, h, w, out[c]);
+            ctx->launches++;
+        }
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
@@ -365,8 +433,9 @@ int check_flags(jxlb200_ctx *ctx) {
     if (!ctx->flags.p) return 0;
     int e[4] = {0, 0, 0, 0};
     CUDA_TRY(ctx, cudaMemcpy(e, ctx->flags.p, sizeof(e), cudaMemcpyDeviceToHost));
-    if (!e[0] && !e[2]) return 0;
+    if (!e[0] && !e[2] && !e[3]) return 0;
     cudaMemset(ctx->flags.p, 0, sizeof(e));
+    if (e[3]) return ctx->fail(JXLB200_E_UNSUPPORTED, "chroma subsampling with varblocks larger than 8x8");
     if (e[2]) return ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select (HFMetadata.java:45-46)");
     return ctx->fail(JXLB200_E_STREAM, "Invalid EPF Sharpness (Frame.java:565-566)");
 }
@@ -434,7 +503,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps};
     for (DevBuf *b : all) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -530,7 +599,8 @@ int32_t jxlb200_vardct_reconstruct_dev(jxlb200_ctx *ctx, const jxlb200_frame_par
     const size_t plane = (size_t)p->width * p->height;
     CUDA_TRY(ctx, ctx->mid.ensure(sizeof(float) * 3 * plane));
     float *mid[3] = {ctx->mid.as<float>(), ctx->mid.as<float>() + plane, ctx->mid.as<float>() + 2 * plane};
-    rc = invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, p->width);
+    rc = is_subsampled(p) ? invert_subsampled_dev(ctx, p, qcoeff, lf, dct_select, hf_mul, mid)
+                          : invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, p->width);
     if (rc) return rc;
     return restore_dev(ctx, p, nullptr, mid, p->width, hf_mul, sharpness, out);
 }
@@ -574,6 +644,29 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int W = p->width, H = p->height, wb = W >> 3, tw = (W + 63) >> 6;
     const size_t npx = (size_t)W * H, nb = npx / 64;
+    if (is_subsampled(p)) {
+        // chroma-subsampled frame: plain upload -> stage 1 per channel + upsampling -> stage 2 -> download
+        CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(int32_t) * npx));
+        CUDA_TRY(ctx, ctx->in_lf.ensure(3 * sizeof(float) * nb));
+        CUDA_TRY(ctx, ctx->mid.ensure(3 * sizeof(float) * npx));
+        CUDA_TRY(ctx, ctx->out_planes.ensure(3 * sizeof(float) * npx));
+        const int32_t *dq[3]; const float *dlf[3]; float *mid[3], *dout[3];
+        for (int c = 0; c < 3; c++) {
+            const size_t nc = (size_t)(W >> p->shift_x[c]) * (H >> p->shift_y[c]);
+            int32_t *qd = ctx->in_q.as<int32_t>() + c * npx;
+            float *ld = ctx->in_lf.as<float>() + c * nb;
+            CUDA_TRY(ctx, cudaMemcpyAsync(qd, qcoeff[c], sizeof(int32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ld, lf[c], sizeof(float) * (nc / 64), cudaMemcpyHostToDevice, ctx->stream));
+            dq[c] = qd; dlf[c] = ld;
+            mid[c] = ctx->mid.as<float>() + c * npx;
+            dout[c] = ctx->out_planes.as<float>() + c * npx;
+        }
+        HostMaps M;
+        if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
+        if ((rc = invert_subsampled_dev(ctx, p, dq, dlf, M.ds, M.hf, mid))) return rc;
+        if ((rc = restore_dev(ctx, p, nullptr, mid, W, M.hf, M.sharp, dout))) return rc;
+        return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
+    }
     CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(int32_t) * npx));
     CUDA_TRY(ctx, ctx->in_lf.ensure(3 * sizeof(float) * nb));
     CUDA_TRY(ctx, ctx->mid.ensure(3 * sizeof(float) * npx));

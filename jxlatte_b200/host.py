@@ -142,7 +142,13 @@ class Reconstructor:
         ds, bo = _c(st["dct_select"], np.uint8), _c(st["block_origin"], np.uint8)
         hm = _c(st["hf_mul"], np.int32)
         xf, bf = _c(st["x_from_y"], np.int32), _c(st["b_from_y"], np.int32)
-        for a, shp, nm in ((q[0], (H, W), "qcoeff"), (lf[0], (hb, wb), "lf"), (ds, (hb, wb), "dct_select"),
+        p = getattr(self, "_p_for_shapes", None)
+        for c in range(3):      # chroma-subsampled channels carry their own (H >> sy) x (W >> sx) planes
+            sy, sx = (p.shift_y[c], p.shift_x[c]) if p is not None else (0, 0)
+            if q[c].shape != (H >> sy, W >> sx) or lf[c].shape != (hb >> sy, wb >> sx):
+                raise ValueError("qcoeff[%d] / lf[%d] have shapes %s / %s, expected %s / %s" % (
+                    c, c, q[c].shape, lf[c].shape, (H >> sy, W >> sx), (hb >> sy, wb >> sx)))
+        for a, shp, nm in ((ds, (hb, wb), "dct_select"),
                            (bo, (hb, wb), "block_origin"), (hm, (hb, wb), "hf_mul"), (xf, (th, tw), "x_from_y"),
                            (bf, (th, tw), "b_from_y")):
             if a.shape != shp:
@@ -189,7 +195,11 @@ class Reconstructor:
     def reconstruct(self, p, st, out=None):
         """The whole path on host buffers: invertVarDCT -> Gaborish -> EPF -> colour transform."""
         H, W = p.height, p.width
-        q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True)
+        self._p_for_shapes = p
+        try:
+            q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True)
+        finally:
+            self._p_for_shapes = None
         if out is None:
             out = np.empty((3, H, W), np.float32)
         self._check(self._L.jxlb200_vardct_reconstruct(

@@ -7,8 +7,9 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import oracle as orc  # noqa: E402
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import oracle as orc  # noqa: E402
 
 from jxlatte_b200 import host  # noqa: E402
 

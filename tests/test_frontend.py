@@ -114,3 +114,22 @@ def test_gpu_decode_matches_oracle_decode(name):
     assert np.array_equal(got.to_int(16), want.to_int(16))
     if name in PINS and "png8" in PINS[name]:
         assert _digest(got.to_int(8)) == PINS[name]["png8"]
+
+
+LOCAL = os.path.join(G, "samples_local")     # larger sample inputs, not committed (tests skip when absent)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ants", "george-tiled", "sollevante-hdr"])
+def test_gpu_decode_matches_oracle_decode_large(name):
+    """BASELINE configs[0] (ants.jxl: JPEG-recompressed, chroma-subsampled YCbCr, raw quant tables), a 135-frame tiled
+    image and a 4K HDR photo: CUDA decode == oracle decode, bit for bit."""
+    from oracle_engine import OracleEngine
+    path = os.path.join(LOCAL, name + ".jxl")
+    if not os.path.exists(path):
+        pytest.skip("sample not present")
+    want = JXLDecoder(path, engine=OracleEngine()).decode()
+    dec = JXLDecoder(path)
+    got = dec.decode()
+    dec.close()
+    assert np.array_equal(got.planes, want.planes)

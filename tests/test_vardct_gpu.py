@@ -174,7 +174,7 @@ def test_invalid_transform_type_is_reported(recon):
         recon.invertVarDCT(p, st)
 
 
-def test_chroma_subsampling_is_unsupported(recon):
+def test_stage1_alone_rejects_chroma_subsampling(recon):
     p = default_frame_params(64, 64)
     p.shift_x[0] = 1
     st = _state(64, 64, 1, default_frame_params(64, 64), mix="dct8")
@@ -188,3 +188,47 @@ def test_bad_arguments(recon):
     st["lf"] = st["lf"][:, :4]
     with pytest.raises(ValueError):
         recon.invertVarDCT(p, st)
+
+
+# ---- chroma-subsampled frames (JPEG recompression) ----
+def _subsampled_state(W, H, shift_y, shift_x, seed):
+    from jxlatte_b200 import synth
+    p = default_frame_params(W, H, epf_iters=0, gab=False, color_mode=2)
+    p.shift_y[:] = shift_y
+    p.shift_x[:] = shift_x
+    qw, qo = qm_generate()
+    st = synth.make_state(W, H, seed=seed, mix=(1.0, 0.0, 0.0, 0.0, 0.0), params=p, qm_weights=qw, qm_offsets=qo)
+    st = dict(st)
+    st["qcoeff"] = [np.ascontiguousarray(st["qcoeff"][c][:H >> shift_y[c], :W >> shift_x[c]]) for c in range(3)]
+    st["lf"] = [np.ascontiguousarray(st["lf"][c][:(H // 8) >> shift_y[c], :(W // 8) >> shift_x[c]]) for c in range(3)]
+    return p, st, qw, qo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shifts", [((1, 0, 1), (1, 0, 1)), ((0, 0, 0), (1, 0, 1)), ((1, 0, 1), (0, 0, 0)), ((0, 1, 1), (1, 1, 0))])
+@pytest.mark.parametrize("filters", [(False, 0), (True, 2)])
+def test_chroma_subsampled_frame_exact(recon, orc, shifts, filters):
+    """4:2:0, 4:2:2, 4:4:0 and a mixed layout: stage 1 per channel on strided block maps + Frame.invertSubsampling."""
+    W, H = 272, 144
+    p, st, qw, qo = _subsampled_state(W, H, shifts[0], shifts[1], seed=0x4A584C00 + 77)
+    p.gab, p.epf_iters = (1 if filters[0] else 0), filters[1]
+    recon.setWeights(qw, qo)
+    got = recon.reconstruct(p, st)
+    want = orc.vardct_reconstruct(p, st, nthreads=4)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_chroma_subsampling_rejects_large_varblocks(recon):
+    from jxlatte_b200 import synth
+    W, H = 256, 256
+    p = default_frame_params(W, H, epf_iters=0, gab=False, color_mode=2)
+    p.shift_y[:] = (1, 0, 1)
+    p.shift_x[:] = (1, 0, 1)
+    qw, qo = qm_generate()
+    st = dict(synth.make_state(W, H, seed=5, params=p, qm_weights=qw, qm_offsets=qo))
+    st["qcoeff"] = [np.ascontiguousarray(st["qcoeff"][c][:H >> p.shift_y[c], :W >> p.shift_x[c]]) for c in range(3)]
+    st["lf"] = [np.ascontiguousarray(st["lf"][c][:(H // 8) >> p.shift_y[c], :(W // 8) >> p.shift_x[c]]) for c in range(3)]
+    recon.setWeights(qw, qo)
+    with pytest.raises(NotImplementedError):
+        recon.reconstruct(p, st)

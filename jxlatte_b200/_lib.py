@@ -62,7 +62,13 @@ SYMBOLS = {
     "jxlb200_modular_rct_dev": (_i32, [_vp, _P3, _i32, _i32, _i32]),
     "jxlb200_modular_palette_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _P3]),
     "jxlb200_modular_squeeze_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "jxlb200_blend": (_i32, [_vp, _vp, _i32, _i32, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64]),
 }
+
+
+class BlendOp(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("is_int", C.c_int32), ("is_alpha", C.c_int32), ("has_extra", C.c_int32),
+                ("clamp", C.c_int32), ("premult", C.c_int32)]
 
 _LIB = None
 

@@ -17,6 +17,7 @@
 #include "k2_exact.cuh"
 #include "k3_modular.cuh"
 #include "k6_subsample.cuh"
+#include "k7_blend.cuh"
 #include "qm_tables.cuh"
 
 // grow-only device allocation
@@ -52,6 +53,7 @@ struct jxlb200_ctx {
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    DevBuf blend;           // five compact rectangles of jxlb200_blend
     DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
     DevTables tab;
 
@@ -503,7 +505,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend};
     for (DevBuf *b : all) b->release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -930,6 +932,42 @@ int32_t jxlb200_modular_palette(jxlb200_ctx *ctx, const int32_t *idx, const int3
     free(outs);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+
+// ---- frame / patch blending on host rectangles (k7_blend.cuh) ----
+int32_t jxlb200_blend(jxlb200_ctx *ctx, const jxlb200_blend_op *op, int32_t h, int32_t w,
+    void *canvas, int64_t canvas_pitch, const void *frame, int64_t frame_pitch, const void *ref, int64_t ref_pitch,
+    const float *frame_alpha, int64_t frame_alpha_pitch, const float *ref_alpha, int64_t ref_alpha_pitch) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!op || !canvas || !frame || !ref || h < 0 || w < 0) return ctx->fail(JXLB200_E_ARG, "NULL pointer or negative size");
+    if (op->mode < 1 || op->mode > 4) return ctx->fail(JXLB200_E_STREAM, "Illegal blend mode");
+    if (h == 0 || w == 0) return 0;
+    int mode = op->mode;
+    if ((mode == 2 || mode == 3) && !op->has_extra) mode = 1;
+    if (op->is_int && mode != 1) return ctx->fail(JXLB200_E_ARG, "integer samples only blend with ADD (the reference casts to float first)");
+    const bool need_fa = (mode == 2 && !op->is_alpha) || mode == 3, need_ra = mode == 2 && !op->is_alpha;
+    if ((need_fa && !frame_alpha) || (need_ra && !ref_alpha)) return ctx->fail(JXLB200_E_ARG, "alpha plane missing");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w, row = sizeof(float) * (size_t)w;
+    CUDA_TRY(ctx, ctx->blend.ensure(5 * sizeof(float) * n));
+    char *base = (char *)ctx->blend.p;
+    cudaStream_t st = ctx->stream;
+    BlendArgs A;
+    A.mode = op->mode; A.is_int = op->is_int; A.is_alpha = op->is_alpha; A.has_extra = op->has_extra; A.clamp = op->clamp; A.premult = op->premult;
+    A.h = h; A.w = w;
+    A.a = base; A.b = base + sizeof(float) * n; A.fa = (const float *)(base + 2 * sizeof(float) * n);
+    A.ra = (const float *)(base + 3 * sizeof(float) * n); A.out = base + 4 * sizeof(float) * n;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync((void *)A.a, row, frame, sizeof(float) * frame_pitch, row, h, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync((void *)A.b, row, ref, sizeof(float) * ref_pitch, row, h, cudaMemcpyHostToDevice, st));
+    if (need_fa) CUDA_TRY(ctx, cudaMemcpy2DAsync((void *)A.fa, row, frame_alpha, sizeof(float) * frame_alpha_pitch, row, h, cudaMemcpyHostToDevice, st));
+    if (need_ra) CUDA_TRY(ctx, cudaMemcpy2DAsync((void *)A.ra, row, ref_alpha, sizeof(float) * ref_alpha_pitch, row, h, cudaMemcpyHostToDevice, st));
+    k7_blend<<<min(ctx->sms * 8, ceil_div((int)std::min<size_t>(n, 1u << 30), 256)), 256, 0, st>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(canvas, sizeof(float) * canvas_pitch, A.out, row, row, h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return 0;
 }
 

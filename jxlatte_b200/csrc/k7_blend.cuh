@@ -1,0 +1,57 @@
+// k7_blend.cuh -- frame / patch blending: JXLCodestreamDecoder.blendAdd / blendMult / blendBlend /
+// blendMulAdd (J/JXLCodestreamDecoder.java:285-413), one rectangle of one channel per launch.  Elementwise and
+// memory-bound; float expressions keep the Java's operand order, uncontracted.
+//   a = the buffer the Java passes as `frame` (indexed at frameOffset), b = the one it passes as `ref` (at refOffset),
+//   fa / ra = frameAlpha at frameOffset / refAlpha at refOffset (floats), out = canvas at patchStart.
+#pragma once
+#include "common.cuh"
+
+struct BlendArgs {
+    int mode, is_int, is_alpha, has_extra, clamp, premult;
+    int h, w;
+    const void *a, *b;
+    const float *fa, *ra;
+    void *out;
+};
+
+__device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }   // MathHelper.clampAsc
+
+__global__ void k7_blend(BlendArgs A) {
+    const long long n = (long long)A.h * A.w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int mode = A.mode;
+        if ((mode == 2 || mode == 3) && !A.has_extra) mode = 1;       // no alpha anywhere: both resolve to blendAdd
+        if (mode == 1) {
+            if (A.is_int) {
+                ((int *)A.out)[i] = (int)((unsigned)((const int *)A.b)[i] + (unsigned)((const int *)A.a)[i]);
+            } else {
+                ((float *)A.out)[i] = __fadd_rn(((const float *)A.b)[i], ((const float *)A.a)[i]);
+            }
+            continue;
+        }
+        const float fs = ((const float *)A.a)[i], rs = ((const float *)A.b)[i];
+        float r;
+        if (mode == 4) {                                               // blendMult
+            const float ns = A.clamp ? clamp01(fs) : fs;
+            r = __fmul_rn(ns, rs);
+        } else if (mode == 2) {                                        // blendBlend
+            const float old_alpha = A.is_alpha ? rs : A.ra[i];
+            float new_alpha = A.is_alpha ? fs : A.fa[i];
+            if (A.clamp) new_alpha = clamp01(new_alpha);
+            if (A.is_alpha) {
+                r = __fadd_rn(old_alpha, __fmul_rn(new_alpha, __fsub_rn(1.0f, old_alpha)));
+            } else if (A.premult) {
+                r = __fadd_rn(fs, __fmul_rn(rs, __fsub_rn(1.0f, new_alpha)));
+            } else {
+                const float num = __fadd_rn(__fmul_rn(fs, new_alpha), __fmul_rn(__fmul_rn(rs, old_alpha), __fsub_rn(1.0f, new_alpha)));
+                const float den = __fadd_rn(old_alpha, __fmul_rn(new_alpha, __fsub_rn(1.0f, old_alpha)));
+                r = __fdiv_rn(num, den);
+            }
+        } else {                                                       // blendMulAdd (the alpha channel itself is a plain copy, done by the caller)
+            float new_alpha = A.fa[i];
+            if (A.clamp) new_alpha = clamp01(new_alpha);
+            r = __fadd_rn(rs, __fmul_rn(new_alpha, fs));
+        }
+        ((float *)A.out)[i] = r;
+    }
+}

@@ -50,6 +50,12 @@ class CudaEngine:
     def modular(self, channels, transforms, bit_depth):
         return self._host.ModularTransforms(self.rec, bit_depth).applyTransforms(channels, transforms)
 
+    def color(self, p, planes):
+        return self.rec.performColorTransforms(p, planes)
+
+    def blend(self, op, canvas, a, b, fa, ra):
+        self.rec.blend(op, canvas, a, b, fa, ra)
+
     def close(self):
         self.rec.close()
 
@@ -87,27 +93,64 @@ def _conversion_matrix(color):
     return (reverse @ adapt @ forward).astype(np.float32)
 
 
-class JXLImage:
-    """Decoded image: `planes` float32 [C, H, W] (colour first, then extra channels), linear light in the tagged primaries
-    for XYB images (what PFMWriter writes), or integer-valued samples scaled to [0, 1] for non-XYB images."""
+class _Buf:
+    """ImageBuffer (J/util/ImageBuffer.java): one channel, int32 or float32, type changed in place by castToFloat so that
+    every alias (canvas, reference slots) sees it."""
 
-    def __init__(self, planes, info, linear):
-        self.planes = planes
+    def __init__(self, a):
+        self.a = a
+
+    @property
+    def is_int(self):
+        return self.a.dtype != np.float32
+
+    def cast_to_float(self, depth):
+        if self.is_int:
+            scale = np.float32(1.0) / np.float32((1 << depth) - 1)
+            self.a = self.a.astype(np.float32) * scale
+
+
+class JXLImage:
+    """Decoded image.  `channels`: one 2-D array per channel (colour first, then extra channels): float32 linear light in
+    the tagged primaries for XYB images (what PFMWriter writes), float32 in [0, 1] for other lossy images, int32 samples for
+    lossless Modular images.  `planes` stacks them (cast to float when the types are mixed)."""
+
+    def __init__(self, channels, info, linear):
+        self.channels = list(channels)
         self.info = info
         self.linear = linear
 
     @property
+    def planes(self):
+        if len({c.dtype for c in self.channels}) == 1:
+            return np.stack(self.channels)
+        return np.stack([self._as_float(i) for i in range(len(self.channels))])
+
+    def _depth(self, i):
+        ncol = self.info["color_channels"]
+        return self.info["bits_per_sample"] if i < ncol else self.info["extra_channels"][i - ncol]["bits_per_sample"]
+
+    def _as_float(self, i):
+        c = self.channels[i]
+        if c.dtype == np.float32:
+            return c
+        return c.astype(np.float32) * (np.float32(1.0) / np.float32((1 << self._depth(i)) - 1))
+
+    @property
     def width(self):
-        return self.planes.shape[2]
+        return self.channels[0].shape[1]
 
     @property
     def height(self):
-        return self.planes.shape[1]
+        return self.channels[0].shape[0]
 
     def to_int(self, bits=8):
         """PNGWriter's sample pipeline: TF_SRGB.fromLinearF for linear images, then (int)(v * max + 0.5f) clamped
-        (J/color/TransferFunction.java:39-43, J/util/ImageBuffer.java:129-145)."""
-        v = self.planes.astype(np.float32)
+        (J/color/TransferFunction.java:39-43, J/util/ImageBuffer.java:129-145).  Integer channels whose depth already is
+        `bits` are only clamped."""
+        if all(c.dtype != np.float32 and self._depth(i) == bits for i, c in enumerate(self.channels)):
+            return np.clip(np.stack(self.channels), 0, (1 << bits) - 1).astype(np.uint16 if bits > 8 else np.uint8)
+        v = np.stack([self._as_float(i) for i in range(len(self.channels))])
         ncol = self.info["color_channels"]
         if self.linear:
             c = v[:ncol]
@@ -136,7 +179,8 @@ class JXLImage:
                     chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
     def write_pfm(self, path):
-        p = self.planes[:3] if self.planes.shape[0] >= 3 else self.planes[:1]
+        v = [self._as_float(i) for i in range(len(self.channels))]
+        p = np.stack(v[:3] if len(v) >= 3 else v[:1])
         with open(path, "wb") as f:
             f.write(("PF\n" if p.shape[0] == 3 else "Pf\n").encode() + ("%d %d\n1.0\n" % (self.width, self.height)).encode())
             f.write(np.moveaxis(p, 0, 2)[::-1].astype(">f4").tobytes())
@@ -210,16 +254,15 @@ class JXLDecoder:
         del keep
         return out
 
+    # ---- one frame: Frame.decodeFrame (+ the colour transform when nothing has to happen in between) ----
     def decode_frame(self, parsed, k):
-        """-> float32 planes [C, h, w] of frame k (frame size, before blending), colour transform applied."""
+        """-> (list of _Buf of frame size: colour channels then extra channels, colour transform still pending?, params)."""
         info, f = parsed.info, parsed.frames[k]
-        if f["flags"] & (FLAG_NOISE | FLAG_PATCHES | FLAG_SPLINES | FLAG_USE_LF_FRAME):
-            raise NotImplementedError("noise / patches / splines / LF frames (flags=%d): SURVEY.md 8f-3/4" % f["flags"])
+        if f["flags"] & (FLAG_NOISE | FLAG_SPLINES | FLAG_USE_LF_FRAME):
+            raise NotImplementedError("noise / splines / LF frames (flags=%d): SURVEY.md 8f-4" % f["flags"])
         if f["upsampling"] != 1 or any(u != 1 for u in f["ec_upsampling"]):
             raise NotImplementedError("upsampling: SURVEY.md 8f-4")
         h, w = f["height"], f["width"]
-        ncol = 3 if (info["xyb_encoded"] or f["encoding"] == ENC_VARDCT) else info["color_channels"]
-        planes = []
         bits = info["bits_per_sample"]
         mod = None
         if f["modular"]["channels"]:
@@ -227,31 +270,129 @@ class JXLDecoder:
                        nb_deltas=t["nb_deltas"], d_pred=t["d_pred"], sp=[(bool(s[0]), bool(s[1]), s[2], s[3]) for s in t["sp"]])
                   for t in f["modular"]["transforms"]]
             mod = self.engine.modular(parsed.modular_channels(k), tr, bits)
+        pending, p = False, None
         if f["encoding"] == ENC_VARDCT:
             st = parsed.vardct_state(k)
             st["qm_weights"], st["qm_offsets"] = self.quant_tables(parsed, k, f)
             p = self.frame_params(info, f)
-            rec = self.engine.reconstruct(p, st)
-            planes = [rec[c][:h, :w] for c in range(3)]
-            linear = bool(info["xyb_encoded"])
-            if not linear:
-                planes = planes        # YCbCr -> RGB already in [0, 1]
+            # patches and saveBeforeCT act on the planes BEFORE the colour transform (JXLCodestreamDecoder.java:611-616)
+            pending = p.color_mode != 0 and (bool(f["flags"] & FLAG_PATCHES) or f["save_before_ct"])
+            if pending:
+                q = p.copy()
+                q.color_mode = 0
+                rec = self.engine.reconstruct(q, st)
+            else:
+                rec = self.engine.reconstruct(p, st)
+            bufs = [_Buf(np.ascontiguousarray(rec[c][:h, :w])) for c in range(3)]
+            first = 0
         else:
             if info["xyb_encoded"]:
                 raise NotImplementedError("XYB-encoded Modular frames")
-            if info["exp_bits"]:
-                raise NotImplementedError("float samples in Modular frames")
-            scale = np.float32(1.0) / np.float32((1 << bits) - 1)
-            planes = [mod[c][:h, :w].astype(np.float32) * scale for c in range(ncol)]
-            linear = False
-        if mod is not None:
-            first = 0 if f["encoding"] == ENC_VARDCT else ncol
-            for e, ec in enumerate(info["extra_channels"]):
-                scale = np.float32(1.0) / np.float32((1 << ec["bits_per_sample"]) - 1)
-                planes.append(mod[first + e][:h, :w].astype(np.float32) * scale)
-        return np.stack(planes), linear
+            if f["do_ycbcr"]:
+                raise NotImplementedError("YCbCr Modular frames")
+            ncol = info["color_channels"]
+            bufs = [_Buf(np.ascontiguousarray(mod[c][:h, :w])) for c in range(ncol)]          # int32 samples (Frame.java:452-455)
+            first = ncol
+        for e in range(len(info["extra_channels"])):
+            bufs.append(_Buf(np.ascontiguousarray(mod[first + e][:h, :w])))
+        return bufs, pending, p
+
+    # ---- JXLCodestreamDecoder.blendBuffers (:415-497) ----
+    def _blend_buffers(self, info, canvas, frame_bufs, ref_bufs, patch_start, frame_offset, ref_offset, size, idx, frame_colors, binfo, patch):
+        colors = info["color_channels"]
+        extras = info["extra_channels"]
+        frame_buf = frame_bufs[(1 if idx == 0 else idx + 2) if colors != frame_colors else idx]
+        ex = idx - colors
+        is_extra, has_extra = ex >= 0, len(extras) > 0
+        is_alpha = is_extra and extras[ex]["type"] == 0
+        mode, alpha_ch, clamp = binfo
+        alpha_info = extras[alpha_ch] if has_extra else None
+        depth = extras[ex]["bits_per_sample"] if is_extra else info["bits_per_sample"]
+        premult = bool(has_extra and alpha_info["alpha_associated"])
+        h, w = size
+
+        def rect(buf, off):
+            v = buf.a[off[0]:off[0] + h, off[1]:off[1] + w]
+            if off[0] < 0 or off[1] < 0 or v.shape != (h, w):
+                raise frontend.InvalidBitstreamError("blend rectangle outside its buffer")
+            return v
+        if canvas.is_int != frame_buf.is_int:
+            frame_buf.cast_to_float(depth)
+            canvas.cast_to_float(depth)
+        if mode == 0 or (ref_bufs is None and mode == 1):
+            rect(canvas, patch_start)[...] = rect(frame_buf, frame_offset)
+            return
+        if ref_bufs is None:
+            raise frontend.InvalidBitstreamError("blending against a reference frame that was never stored")
+        if ref_bufs[idx] is None:
+            ref_bufs[idx] = _Buf(np.zeros(canvas.a.shape, canvas.a.dtype))
+        ref_buf = ref_bufs[idx]
+        ref_alpha = ref_bufs[colors + alpha_ch] if has_extra else None
+        frame_alpha = frame_bufs[frame_colors + alpha_ch] if has_extra else None
+        if has_extra and mode in (2, 3):
+            adepth = alpha_info["bits_per_sample"]
+            if mode == 2:
+                if ref_alpha is None:
+                    ref_alpha = _Buf(np.zeros(canvas.a.shape, np.float32))
+                    ref_bufs[colors + alpha_ch] = ref_alpha
+                ref_alpha.cast_to_float(adepth)
+            frame_alpha.cast_to_float(adepth)
+        should_cast = mode == 4 or (mode == 2 and has_extra) or (mode == 3 and has_extra and not is_alpha)
+        if should_cast or ref_buf.is_int != frame_buf.is_int:
+            frame_buf.cast_to_float(depth)
+            canvas.cast_to_float(depth)
+            ref_buf.cast_to_float(depth)
+        below = False
+        if patch:
+            if mode == 5:
+                mode, below = 2, True
+            elif mode == 6:
+                mode = 3
+            elif mode == 7:
+                mode, below = 3, True
+            else:
+                mode -= 1
+        old_buf, new_buf = (ref_buf, frame_buf) if below else (frame_buf, ref_buf)     # passed as the Java's `frame`, `ref`
+        if mode == 3 and has_extra and is_alpha:
+            rect(canvas, patch_start)[...] = rect(new_buf, frame_offset)                # copyToCanvas(..., ref), :389-391
+            return
+        if mode < 1 or mode > 4:
+            raise frontend.InvalidBitstreamError("Illegal blend mode")
+        eff = 1 if (mode in (2, 3) and not has_extra) else mode
+        need_fa = (eff == 2 and not is_alpha) or eff == 3
+        need_ra = eff == 2 and not is_alpha
+        op = dict(mode=mode, is_int=int(canvas.is_int), is_alpha=int(is_alpha), has_extra=int(has_extra), clamp=int(clamp), premult=int(premult))
+        if eff == 1 and not (canvas.is_int == old_buf.is_int == new_buf.is_int):
+            raise frontend.InvalidBitstreamError("blendAdd over buffers of different types")
+        self.engine.blend(op, rect(canvas, patch_start), rect(old_buf, frame_offset), rect(new_buf, ref_offset),
+                          rect(frame_alpha, frame_offset) if need_fa else None, rect(ref_alpha, ref_offset) if need_ra else None)
+
+    # ---- JXLCodestreamDecoder.computePatches (:212-254) ----
+    def _compute_patches(self, info, f, frame_bufs, frame_colors, reference):
+        colors, nextra = info["color_channels"], len(info["extra_channels"])
+        for patch in f["patches"]:
+            if patch["ref"] > 3:
+                raise frontend.InvalidBitstreamError("Patch out of range")
+            ref = reference[patch["ref"]]
+            if ref is None:
+                continue
+            if patch["y0"] + patch["h"] > ref[0].a.shape[0] or patch["x0"] + patch["w"] > ref[0].a.shape[1]:
+                raise frontend.InvalidBitstreamError("Patch too large")
+            npos = len(patch["pos"]) // 2
+            for j in range(npos):
+                x0, y0 = patch["pos"][2 * j], patch["pos"][2 * j + 1]
+                if y0 < 0 or x0 < 0 or patch["h"] + y0 > f["height"] or patch["w"] + x0 > f["width"]:
+                    raise frontend.InvalidBitstreamError("Patch size out of bounds")
+                for d in range(colors + nextra):
+                    c = 0 if d < colors else d - colors + 1
+                    b = patch["blend"][3 * (j * (nextra + 1) + c):3 * (j * (nextra + 1) + c) + 3]
+                    if b[0] == 0:
+                        continue
+                    self._blend_buffers(info, frame_bufs[d], frame_bufs, ref, (y0, x0), (y0, x0), (patch["y0"], patch["x0"]),
+                                        (patch["h"], patch["w"]), d, frame_colors, (b[0], b[1], bool(b[2])), True)
 
     def decode(self):
+        """JXLCodestreamDecoder.decode's frame loop (:588-626) for the features this build renders."""
         import time
         t0 = time.perf_counter()
         parsed = frontend.parse(self.data)
@@ -259,36 +400,66 @@ class JXLDecoder:
         if self.engine is None:
             self.engine = CudaEngine()
         info = parsed.info
-        canvas, linear = None, False
+        colors, nextra = info["color_channels"], len(info["extra_channels"])
+        canvas = None                      # list of _Buf
+        reference = [None, None, None, None]
+        linear = bool(info["xyb_encoded"])
         t1 = time.perf_counter()
         for k, f in enumerate(parsed.frames):
-            if f["type"] in (1, 2):
-                raise NotImplementedError("LF frames / reference-only frames: SURVEY.md 8f-3")
-            planes, linear = self.decode_frame(parsed, k)
+            if f["type"] == 1 or f["lf_level"] > 0:
+                raise NotImplementedError("LF frames: SURVEY.md 8f-3")
+            bufs, pending, p = self.decode_frame(parsed, k)
+            frame_colors = 3 if (info["xyb_encoded"] or f["encoding"] == ENC_VARDCT) else colors
+            save = (f["save_as_reference"] != 0 or f["duration"] == 0) and not f["is_last"] and f["type"] != 1
+            if save and f["save_before_ct"]:
+                reference[f["save_as_reference"]] = [_Buf(b.a.copy()) for b in bufs]
+            self._compute_patches(info, f, bufs, frame_colors, reference)
+            if pending:
+                rgb = self.engine.color(p, np.stack([bufs[c].a for c in range(3)]))
+                for c in range(3):
+                    bufs[c] = _Buf(np.ascontiguousarray(rgb[c]))
             if canvas is None:
-                canvas = np.zeros((planes.shape[0], info["height"], info["width"]), np.float32)
-            if f["blend_mode"] != 0:
-                raise NotImplementedError("blend mode %d: SURVEY.md 8f-3" % f["blend_mode"])
-            y0, x0 = f["y0"], f["x0"]
-            ys, xs = max(0, y0), max(0, x0)
-            ye, xe = min(info["height"], y0 + planes.shape[1]), min(info["width"], x0 + planes.shape[2])
-            if ye > ys and xe > xs:
-                canvas[:, ys:ye, xs:xe] = planes[:, ys - y0:ye - y0, xs - x0:xe - x0]
+                dt = bufs[0].a.dtype
+                canvas = [_Buf(np.zeros((info["height"], info["width"]), dt)) for _ in range(colors + nextra)]
+            if f["type"] in (0, 3):
+                aliased = any(reference[i] is canvas and i != f["save_as_reference"] for i in range(4))
+                if aliased:
+                    canvas = [_Buf(b.a.copy()) for b in canvas]
+                # blendFrame (:499-523)
+                ih, iw = info["height"], info["width"]
+                ps = (min(max(f["y0"], 0), ih), min(max(f["x0"], 0), iw))
+                fo = (ps[0] - f["y0"], ps[1] - f["x0"])
+                size = (min(f["y0"] + f["height"], ih) - ps[0], min(f["x0"] + f["width"], iw) - ps[1])
+                if size[0] > 0 and size[1] > 0:
+                    for c in range(len(canvas)):
+                        if c >= colors:
+                            m, a, cl, src = f["ec_blending"][c - colors]
+                        else:
+                            m, a, cl, src = f["blend_mode"], f["blend_alpha"], f["blend_clamp"], f["blend_source"]
+                        self._blend_buffers(info, canvas[c], bufs, reference[src], ps, fo, ps, size, c, frame_colors, (m, a, bool(cl)), False)
+            if save and not f["save_before_ct"]:
+                reference[f["save_as_reference"]] = canvas
         self.timings["reconstruct_s"] = time.perf_counter() - t1
         o = info["orientation"]
-        if o != 1:                    # JXLCodestreamDecoder.transposeBuffer
-            if o in (2, 3):
-                canvas = canvas[:, :, ::-1] if o == 2 else canvas[:, ::-1, ::-1]
-            elif o == 4:
-                canvas = canvas[:, ::-1, :]
-            elif o == 5:
-                canvas = canvas.transpose(0, 2, 1)
-            elif o == 6:
-                canvas = canvas.transpose(0, 2, 1)[:, :, ::-1]
-            elif o == 7:
-                canvas = canvas[:, ::-1, ::-1].transpose(0, 2, 1)
-            else:
-                canvas = canvas.transpose(0, 2, 1)[:, ::-1, :]
-            canvas = np.ascontiguousarray(canvas)
+        out = []
+        for b in canvas:
+            a = b.a
+            if o != 1:                    # JXLCodestreamDecoder.transposeBuffer (:43-112)
+                if o == 2:
+                    a = a[:, ::-1]
+                elif o == 3:
+                    a = a[::-1, ::-1]
+                elif o == 4:
+                    a = a[::-1, :]
+                elif o == 5:
+                    a = a.T
+                elif o == 6:
+                    a = a.T[:, ::-1]
+                elif o == 7:
+                    a = a[::-1, ::-1].T
+                else:
+                    a = a.T[::-1, :]
+                a = np.ascontiguousarray(a)
+            out.append(a)
         parsed.close()
-        return JXLImage(canvas, info, linear)
+        return JXLImage(out, info, linear)

@@ -106,6 +106,24 @@ void describe(jxlf_image &im) {
         j.num("color_factor", f.color_factor); j.flt("base_corr_x", f.base_corr_x); j.flt("base_corr_b", f.base_corr_b);
         j.num("x_factor_lf", f.x_factor_lf); j.num("b_factor_lf", f.b_factor_lf);
         j.farr("noise", f.noise, f.noise + 8); j.num("num_patches", f.num_patches); j.num("num_splines", f.num_splines);
+        j.open("patches", '[');
+        for (auto &pt : f.patches) {
+            j.open(nullptr, '{');
+            j.num("ref", pt.ref); j.num("x0", pt.x0); j.num("y0", pt.y0); j.num("w", pt.w); j.num("h", pt.h);
+            j.iarr("pos", pt.pos.begin(), pt.pos.end()); j.iarr("blend", pt.blend.begin(), pt.blend.end());
+            j.close('}');
+        }
+        j.close(']');
+        j.open("ec_blending", '[');
+        for (auto &b : h.ec_blending) {
+            j.open(nullptr, '[');
+            j.sep(); j.o << b.mode;
+            j.sep(); j.o << b.alpha_channel;
+            j.sep(); j.o << (b.clamp ? 1 : 0);
+            j.sep(); j.o << b.source;
+            j.close(']');
+        }
+        j.close(']');
         j.boolean("decoded", !f.dct_select.empty() || f.has_modular || h.encoding == ENC_MODULAR);
         j.boolean("quant_all_default", f.quant_all_default);
         if (!f.quant_all_default) {

@@ -33,7 +33,9 @@ struct QuantParams {
     std::vector<float> raw[3];
 };
 
-struct PatchInfo { int ref, x0, y0, w, h; std::vector<int32_t> pos; std::vector<int32_t> blend; };   // parsed, not rendered
+// Patch.readPatch (J/frame/features/Patch.java:18-60): pos = (x, y) per position; blend = (mode, alpha channel, clamp) per position
+// and per channel group (colour, then each extra channel)
+struct PatchInfo { int ref = 0, x0 = 0, y0 = 0, w = 0, h = 0; std::vector<int32_t> pos; std::vector<int32_t> blend; };
 
 struct FrameData {
     FrameHeader hdr;
@@ -46,6 +48,7 @@ struct FrameData {
     float base_corr_x = 0.0f, base_corr_b = 1.0f;
     float noise[8] = {0};
     int num_patches = 0, num_splines = 0;
+    std::vector<PatchInfo> patches;
     // VarDCT state, frame level
     std::vector<int32_t> qcoeff[3];
     std::vector<float> lf[3];
@@ -190,18 +193,39 @@ class FrameDecoder {
             for (auto &e : ih_.extra) alpha_channels += e.type == 0;
             EntropyStream es(br, 10);
             f.num_patches = (int)es.read(br, 0);
-            for (int i = 0; i < f.num_patches; i++) {
-                es.read(br, 1); es.read(br, 3); es.read(br, 3); es.read(br, 2); es.read(br, 2);
+            f.patches.resize(f.num_patches);
+            for (PatchInfo &pt : f.patches) {
+                pt.ref = (int)es.read(br, 1);
+                pt.x0 = (int)es.read(br, 3);
+                pt.y0 = (int)es.read(br, 3);
+                pt.w = 1 + (int)es.read(br, 2);
+                pt.h = 1 + (int)es.read(br, 2);
                 const uint32_t count = 1 + es.read(br, 7);
                 if ((int32_t)count <= 0) throw StreamError("patch count overflow");
+                int32_t px = 0, py = 0;
                 for (uint32_t j = 0; j < count; j++) {
-                    es.read(br, j == 0 ? 4 : 6);
-                    es.read(br, j == 0 ? 4 : 6);
+                    if (j == 0) {
+                        px = (int32_t)es.read(br, 4);
+                        py = (int32_t)es.read(br, 4);
+                    } else {
+                        const int32_t dx = unpack_signed(es.read(br, 6)), dy = unpack_signed(es.read(br, 6));
+                        px = detail::wrap_add(dx, px);
+                        py = detail::wrap_add(dy, py);
+                    }
+                    pt.pos.push_back(px);
+                    pt.pos.push_back(py);
                     for (int k = 0; k < extra + 1; k++) {
                         const uint32_t mode = es.read(br, 5);
                         if (mode >= 8) throw StreamError("illegal patch blend mode");
-                        if (mode > 3 && alpha_channels > 1 && (int)es.read(br, 8) >= extra) throw StreamError("patch alpha channel out of range");
-                        if (mode > 2) es.read(br, 9);
+                        int32_t alpha = 0, clamp = 0;
+                        if (mode > 3 && alpha_channels > 1) {
+                            alpha = (int32_t)es.read(br, 8);
+                            if (alpha >= extra) throw StreamError("patch alpha channel out of range");
+                        }
+                        if (mode > 2) clamp = es.read(br, 9) != 0;
+                        pt.blend.push_back((int32_t)mode);
+                        pt.blend.push_back(alpha);
+                        pt.blend.push_back(clamp);
                     }
                 }
             }

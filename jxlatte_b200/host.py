@@ -220,6 +220,22 @@ class Reconstructor:
         self._check(self._L.jxlb200_restore_dev(self._h, C.byref(p), C.byref(slab) if slab is not None else None,
                                                 _lib.planes(xyb), int(pitch), hm, sh, _lib.planes(out)))
 
+    # -- blending (JXLCodestreamDecoder.blendAdd / blendMult / blendBlend / blendMulAdd) --
+    def blend(self, op, canvas, a, b, fa=None, ra=None):
+        """One rectangle of one channel; op = dict(mode, is_int, is_alpha, has_extra, clamp, premult); canvas, a (the Java's
+        `frame` argument), b (`ref`), fa / ra (frame / reference alpha) are equally sized 2-D numpy views with contiguous
+        rows; canvas is written in place and may alias a or b."""
+        def rect(v):
+            if v is None:
+                return None, 0
+            if v.ndim != 2 or v.shape != canvas.shape or (v.shape[1] > 1 and v.strides[1] != v.itemsize) or v.itemsize != 4:
+                raise ValueError("blend operands must be equally sized 2-D views of 4-byte samples with contiguous rows")
+            return C.c_void_p(v.ctypes.data), v.strides[0] // v.itemsize
+        o = _lib.BlendOp(int(op["mode"]), int(op["is_int"]), int(op["is_alpha"]), int(op["has_extra"]), int(op["clamp"]), int(op["premult"]))
+        h, w = canvas.shape
+        (cp, cpi), (ap, api), (bp, bpi), (fp, fpi), (rp, rpi) = rect(canvas), rect(a), rect(b), rect(fa), rect(ra)
+        self._check(self._L.jxlb200_blend(self._h, C.byref(o), h, w, cp, cpi, ap, api, bp, bpi, fp, fpi, rp, rpi))
+
     # -- Modular --
     def inverseRCT(self, channels, rct_type):
         """ModularStream.applyTransforms RCT branch: three equal-size channels, returns them as the reference leaves

@@ -92,6 +92,9 @@ void orc_color(const orc_frame_params *p, float *const buf[3], int32_t nthreads)
 
 /* Whole path: invert -> gab -> epf -> color.  out[3] receives the final planes. */
 void orc_invert_subsampling(const orc_frame_params *p, const float *const in[3], float *const out[3]);
+int32_t orc_blend(int32_t mode, int32_t is_int, int32_t is_alpha, int32_t has_extra, int32_t clamp, int32_t premult,
+    int32_t h, int32_t w, void *canvas, int64_t cp, const void *a, int64_t ap, const void *b, int64_t bp,
+    const float *fa, int64_t fap, const float *ra, int64_t rap);
 int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,

@@ -309,3 +309,25 @@ def modular_forward_squeeze(x, horizontal):
 
 def tendency(a, b, c):
     return int(lib().orc_tendency(int(a), int(b), int(c)))
+
+
+def _rect(a):
+    """(pointer to the first element, pitch in elements) of a 2-D view whose rows are contiguous."""
+    if a is None:
+        return None, 0
+    assert a.ndim == 2 and (a.shape[1] <= 1 or a.strides[1] == a.itemsize) and a.strides[0] % a.itemsize == 0
+    return C.c_void_p(a.ctypes.data), a.strides[0] // a.itemsize
+
+
+def blend(op, canvas, a, b, fa=None, ra=None):
+    """JXLCodestreamDecoder.blend* on one rectangle; op = dict(mode, is_int, is_alpha, has_extra, clamp, premult); the
+    arguments are equally sized 2-D numpy views (canvas is written in place)."""
+    L = lib()
+    L.orc_blend.argtypes = [C.c_int32] * 8 + [C.c_void_p, C.c_int64] * 5
+    L.orc_blend.restype = C.c_int32
+    h, w = canvas.shape
+    (cp, cpi), (ap, api), (bp, bpi), (fp, fpi), (rp, rpi) = _rect(canvas), _rect(a), _rect(b), _rect(fa), _rect(ra)
+    rc = L.orc_blend(op["mode"], op["is_int"], op["is_alpha"], op["has_extra"], op["clamp"], op["premult"], h, w,
+                     cp, cpi, ap, api, bp, bpi, fp, fpi, rp, rpi)
+    if rc:
+        raise RuntimeError("orc_blend rc=%d" % rc)

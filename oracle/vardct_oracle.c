@@ -1260,3 +1260,48 @@ int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     orc_color(p, out, nthreads);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame / patch blending  (J/JXLCodestreamDecoder.java:285-413): blendAdd, blendMult, blendBlend, blendMulAdd on one
+ * rectangle of one channel.  a = the Java's `frame` argument at frameOffset, b = its `ref` argument at refOffset.
+ * ---------------------------------------------------------------------------------------------- */
+static float clamp_asc(float v, float lo, float hi) { return v < lo ? lo : v > hi ? hi : v; }
+
+int32_t orc_blend(int32_t mode, int32_t is_int, int32_t is_alpha, int32_t has_extra, int32_t clamp, int32_t premult,
+    int32_t h, int32_t w, void *canvas, int64_t cp, const void *a, int64_t ap, const void *b, int64_t bp,
+    const float *fa, int64_t fap, const float *ra, int64_t rap) {
+    if (mode < 1 || mode > 4) return -2;
+    if ((mode == 2 || mode == 3) && !has_extra) mode = 1;
+    if (is_int && mode != 1) return -1;
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            if (mode == 1) {
+                if (is_int)
+                    ((int32_t *)canvas)[y * cp + x] = ((const int32_t *)b)[y * bp + x] + ((const int32_t *)a)[y * ap + x];
+                else
+                    ((float *)canvas)[y * cp + x] = ((const float *)b)[y * bp + x] + ((const float *)a)[y * ap + x];
+                continue;
+            }
+            float *cf = (float *)canvas + y * cp + x;
+            const float ff = ((const float *)a)[y * ap + x], rf = ((const float *)b)[y * bp + x];
+            if (mode == 4) {
+                float newSample = ff;
+                if (clamp) newSample = clamp_asc(newSample, 0.0f, 1.0f);
+                *cf = newSample * rf;
+            } else if (mode == 2) {
+                float oldSample = rf, newSample = ff;
+                float oldAlpha = is_alpha ? oldSample : ra[y * rap + x];
+                float newAlpha = is_alpha ? newSample : fa[y * fap + x];
+                if (clamp) newAlpha = clamp_asc(newAlpha, 0.0f, 1.0f);
+                if (is_alpha) *cf = oldAlpha + newAlpha * (1.0f - oldAlpha);
+                else if (premult) *cf = newSample + oldSample * (1.0f - newAlpha);
+                else *cf = (newSample * newAlpha + oldSample * oldAlpha * (1.0f - newAlpha)) / (oldAlpha + newAlpha * (1.0f - oldAlpha));
+            } else {
+                float oldSample = rf, newSample = ff, newAlpha = fa[y * fap + x];
+                if (clamp) newAlpha = clamp_asc(newAlpha, 0.0f, 1.0f);
+                *cf = oldSample + newAlpha * newSample;
+            }
+        }
+    }
+    return 0;
+}

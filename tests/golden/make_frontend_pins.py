@@ -20,17 +20,17 @@ def dg(a):
 
 
 pins = {}
-for name in ("lenna", "bbb", "white", "bench", "quilt", "art"):
+for name in ("lenna", "bbb", "white", "bench", "quilt", "art", "patches-lossless", "blendmodes_5"):
     path = os.path.join(HERE, "samples", name + ".jxl")
     p = frontend.parse_file(path)
-    i, f = p.info, p.frames[0]
+    i, f = p.info, p.frames[-1]
     e = {"image": [i["width"], i["height"], i["xyb_encoded"], i["orientation"]],
          "frame": [f["encoding"], f["width"], f["height"], f["gab"], f["epf_iters"], f["num_groups"]]}
     if f["encoding"] == 0:
-        st = p.vardct_state(0)
+        st = p.vardct_state(len(p.frames) - 1)
         e["state"] = {k: dg(st[k]) for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
     else:
-        e["modular"] = [dg(c) for c in p.modular_channels(0)]
+        e["modular"] = [dg(c) for c in p.modular_channels(len(p.frames) - 1)]
     img = JXLDecoder(path, engine=OracleEngine()).decode()
     e["png8"] = dg(img.to_int(8))
     pins[name] = e

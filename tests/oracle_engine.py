@@ -47,5 +47,11 @@ class OracleEngine:
     def modular(self, channels, transforms, bit_depth):
         return host.ModularTransforms(_OracleModularOps(), bit_depth).applyTransforms(channels, transforms)
 
+    def color(self, p, planes):
+        return orc.color(p, planes, nthreads=self.nthreads)
+
+    def blend(self, op, canvas, a, b, fa, ra):
+        orc.blend(op, canvas, a, b, fa, ra)
+
     def close(self):
         pass

@@ -170,7 +170,7 @@ bool is_subsampled(const jxlb200_frame_params *p) {
 // stage 1 on device pointers
 int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *const q[3], const float *const lf[3],
                const uint8_t *ds, const uint8_t *bo, const int32_t *hf_mul, const int32_t *xfy, const int32_t *bfy,
-               float *const out[3], long long pitch) {
+               float *const out[3], long long pitch, bool fanout = true) {
     if (is_subsampled(p)) return ctx->fail(JXLB200_E_UNSUPPORTED, "stage 1 alone does not take chroma-subsampled frames: use jxlb200_vardct_reconstruct[_dev]");
     if (!ctx->have_weights) return ctx->fail(JXLB200_E_ARG, "jxlb200_set_qm_weights has not been called");
     const int W = p->width, H = p->height, wb = W >> 3, hb = H >> 3, tw = (W + 63) >> 6, th = (H + 63) >> 6;
@@ -211,6 +211,17 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
 
     // fan out: small | medium | four line-length classes of the big kernels (pass 0, then pass 1 once every pass 0 is done:
     // a varblock's row pass runs in the class of its width, its column pass in the class of its height)
+    if (!fanout) {
+        // one stream: used by the slab-pipelined host entry point, where PCIe (not stage 1) is the bottleneck and the ~40
+        // event calls per slab of the fan-out cost more host time than the overlap wins
+        k1_small<<<min(ctx->sms * 8, ceil_div(ncells, SMALL_BATCH)), 128, 0, st>>>(P, S, ctx->items.as<int>());
+        k1_medium<<<min(ctx->sms * 4, ceil_div(ncells, 2)), 256, 0, st>>>(P, S, ctx->items.as<int>());
+        ctx->launches += 2;
+        launch_big<256, 0>(ctx, P, 3, st); launch_big<128, 0>(ctx, P, 2, st); launch_big<64, 0>(ctx, P, 1, st); launch_big<32, 0>(ctx, P, 0, st);
+        launch_big<128, 1>(ctx, P, 2, st); launch_big<256, 1>(ctx, P, 3, st); launch_big<64, 1>(ctx, P, 1, st); launch_big<32, 1>(ctx, P, 0, st);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    }
     cudaStream_t *ks = ctx->k1_stream;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
     for (int i = 0; i < 6; i++) CUDA_TRY(ctx, cudaStreamWaitEvent(ks[i], ctx->ev_fork, 0));
@@ -632,7 +643,9 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 // 2) -- PCIe is full duplex, so the call costs about max(upload, download, compute) instead of their sum.  Stage 2 of a
 // slab needs HALO rows of the next slab's stage-1 output, hence the one-slab lag; the planes are contiguous on the
 // device, so "halo rows" are simply the neighbouring slab's rows (jxlb200_slab with has_top / has_bottom).
-#define JXLB200_PIPE_ROWS 512
+#ifndef JXLB200_PIPE_ROWS
+#define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; PCIe floor (398 MB each way, duplex) 8.6 ms */
+#endif
 int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
@@ -688,6 +701,8 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
         rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M);
         ctx->stream = keep;
         if (rc) return rc;
+        for (int c = 0; c < 3; c++)      // the LF planes are 1/64 of the coefficients: whole, up front
+            CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * nb, cudaMemcpyHostToDevice, up));
     }
     const int nslab = ceil_div(H, JXLB200_PIPE_ROWS);
     std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);
@@ -703,7 +718,6 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
             const int y0 = slab_y0(i), rows = slab_rows(i);
             for (int c = 0; c < 3 && !rc; c++) {
                 cudaError_t e = cudaMemcpyAsync(dq[c] + (size_t)y0 * W, qcoeff[c] + (size_t)y0 * W, sizeof(int32_t) * (size_t)rows * W, cudaMemcpyHostToDevice, up);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(dlf[c] + (size_t)(y0 / 8) * wb, lf[c] + (size_t)(y0 / 8) * wb, sizeof(float) * (size_t)(rows / 8) * wb, cudaMemcpyHostToDevice, up);
                 if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (upload)", e);
             }
             if (rc) break;
@@ -716,7 +730,7 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
             const float *l3[3] = {dlf[0] + (size_t)(y0 / 8) * wb, dlf[1] + (size_t)(y0 / 8) * wb, dlf[2] + (size_t)(y0 / 8) * wb};
             float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
             rc = invert_dev(ctx, &ps, q3, l3, M.ds + (size_t)(y0 / 8) * wb, M.bo + (size_t)(y0 / 8) * wb, M.hf + (size_t)(y0 / 8) * wb,
-                            M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W);
+                            M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W, false);
             if (rc) break;
         }
         if (i >= 1) {

@@ -169,3 +169,28 @@ def test_blend_kernel_matches_oracle(recon):
     assert np.array_equal(got, want)
     with pytest.raises(ValueError):
         recon.blend(dict(op, mode=4), got, ia[:h, :w], ib[:h, :w])
+
+
+def test_mutated_inputs_never_crash():
+    """Bit flips, truncations and overwritten runs: the C++ front end must come back with a status, not a crash or a hang
+    (run under -fsanitize=address,undefined when the fixtures were made: clean)."""
+    rng = np.random.default_rng(2024)
+    seen = set()
+    for name in ("lenna", "white", "quilt", "art", "blendmodes_5", "patches-lossless"):
+        data = open(os.path.join(S, name + ".jxl"), "rb").read()
+        for i in range(25 if len(data) > 1000 else 60):
+            m = bytearray(data)
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 5))):
+                    m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                m = m[:int(rng.integers(0, len(m)))]
+            else:
+                at = int(rng.integers(0, len(m)))
+                m[at:at + 8] = bytes(rng.integers(0, 256, min(8, len(m) - at), dtype=np.uint8).tolist())
+            p = frontend.parse(bytes(m), strict=False)
+            assert p.status in (0, -1, -2, -3)
+            seen.add(p.status)
+            p.close()
+    assert -2 in seen

@@ -18,6 +18,8 @@
 #include "k3_modular.cuh"
 #include "k6_subsample.cuh"
 #include "k7_blend.cuh"
+#include "k8_features.cuh"
+#include "splines_host.cuh"
 #include "qm_tables.cuh"
 
 // grow-only device allocation
@@ -981,6 +983,102 @@ int32_t jxlb200_blend(jxlb200_ctx *ctx, const jxlb200_blend_op *op, int32_t h, i
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpy2DAsync(canvas, sizeof(float) * canvas_pitch, A.out, row, row, h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+
+// ---- k x k upsampling of one float channel on host buffers (k8_features.cuh) ----
+int32_t jxlb200_upsample(jxlb200_ctx *ctx, const float *in, int32_t h, int32_t w, int32_t k, const float *weights, float *out) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!in || !weights || !out || h <= 0 || w <= 0) return ctx->fail(JXLB200_E_ARG, "NULL pointer or empty channel");
+    if (k != 2 && k != 4 && k != 8) return ctx->fail(JXLB200_E_ARG, "upsampling factor must be 2, 4 or 8 (FrameHeader.java:121-123)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w, nw = (size_t)k * k * 25;
+    CUDA_TRY(ctx, ctx->blend.ensure(sizeof(float) * (n + n * k * k + nw)));
+    float *d_in = ctx->blend.as<float>(), *d_out = d_in + n, *d_w = d_out + n * k * k;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_w, weights, sizeof(float) * nw, cudaMemcpyHostToDevice, st));
+    k8_upsample<<<min(ctx->sms * 8, ceil_div((int)std::min<size_t>(n, 1u << 30), 128)), 128, sizeof(float) * nw, st>>>(d_in, h, w, k, d_w, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, sizeof(float) * n * k * k, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+
+// ---- noise synthesis on host planes (k8_features.cuh): Frame.initializeNoise + synthesizeNoise ----
+int32_t jxlb200_noise(jxlb200_ctx *ctx, float *const planes[3], int32_t h, int32_t w, int32_t group_dim, int64_t seed0,
+    const float lut[8], float base_corr_x, float base_corr_b) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!planes || !planes[0] || !planes[1] || !planes[2] || !lut || h <= 0 || w <= 0) return ctx->fail(JXLB200_E_ARG, "NULL pointer or empty frame");
+    if (group_dim != 128 && group_dim != 256 && group_dim != 512 && group_dim != 1024) return ctx->fail(JXLB200_E_ARG, "group_dim must be 128 << 0..3");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w;
+    CUDA_TRY(ctx, ctx->blend.ensure(sizeof(float) * 6 * n));
+    NoiseArgs A;
+    for (int c = 0; c < 3; c++) { A.local[c] = ctx->blend.as<float>() + c * n; A.plane[c] = ctx->blend.as<float>() + (3 + c) * n; }
+    A.h = h; A.w = w; A.group_dim = group_dim;
+    A.log_dim = group_dim == 128 ? 7 : group_dim == 256 ? 8 : group_dim == 512 ? 9 : 10;
+    A.group_cols = ceil_div(w, group_dim);
+    A.num_groups = A.group_cols * ceil_div(h, group_dim);
+    A.seed0 = (unsigned long long)seed0;
+    for (int i = 0; i < 8; i++) A.lut[i] = lut[i];
+    A.base_x = base_corr_x; A.base_b = base_corr_b;
+    cudaStream_t st = ctx->stream;
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(A.plane[c], planes[c], sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    k8_noise_rng<<<ceil_div(A.num_groups * 8, 64), 64, 0, st>>>(A);
+    k8_noise_apply<<<min(ctx->sms * 8, ceil_div((int)std::min<size_t>(n, 1u << 30), 256)), 256, 0, st>>>(A);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(planes[c], A.plane[c], sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+
+// ---- splines on host planes (splines_host.cuh + k8_splines): Frame.renderSplines ----
+int32_t jxlb200_splines(jxlb200_ctx *ctx, float *const planes[3], int32_t h, int32_t w, int32_t num_splines, const int32_t *npoints,
+    const int32_t *points, const int32_t *coeff, int32_t quant_adjust, float base_corr_x, float base_corr_b) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!planes || !planes[0] || !planes[1] || !planes[2] || !npoints || !points || !coeff || h <= 0 || w <= 0 || num_splines < 0)
+        return ctx->fail(JXLB200_E_ARG, "NULL pointer or empty frame");
+    if (num_splines == 0) return 0;
+    // Spline.computeCoeffs with splineID 0 (see splines_host.cuh)
+    splines_host::Track trk[4];
+    {
+        const float qa = quant_adjust / 8.0f;
+        const float inv_qa = qa >= 0 ? 1.0f / (1.0f + qa) : 1.0f - qa;
+        const float ya = 0.106066017f * inv_qa, xa = 0.005939697f * inv_qa, ba = 0.098994949f * inv_qa, sa = 0.47135738f * inv_qa;
+        for (int i = 0; i < 32; i++) {
+            trk[1].c[i] = coeff[32 + i] * ya;
+            trk[0].c[i] = coeff[i] * xa + base_corr_x * trk[1].c[i];
+            trk[2].c[i] = coeff[64 + i] * ba + base_corr_b * trk[1].c[i];
+            trk[3].c[i] = coeff[96 + i] * sa;
+        }
+    }
+    std::vector<SplineArcDev> arcs;
+    const int32_t *pts = points;
+    for (int s = 0; s < num_splines; s++) {
+        if (npoints[s] < 1) return ctx->fail(JXLB200_E_ARG, "a spline needs at least one control point");
+        splines_host::build(pts, npoints[s], trk, h, w, arcs);
+        pts += 2 * npoints[s];
+    }
+    if (arcs.empty()) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w, abytes = sizeof(SplineArcDev) * arcs.size();
+    CUDA_TRY(ctx, ctx->blend.ensure(sizeof(float) * 3 * n + abytes + 64));
+    float *d[3] = {ctx->blend.as<float>(), ctx->blend.as<float>() + n, ctx->blend.as<float>() + 2 * n};
+    SplineArcDev *d_arcs = (SplineArcDev *)(ctx->blend.as<char>() + ((sizeof(float) * 3 * n + 63) & ~(size_t)63));
+    cudaStream_t st = ctx->stream;
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(d[c], planes[c], sizeof(float) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_arcs, arcs.data(), abytes, cudaMemcpyHostToDevice, st));
+    k8_splines<<<dim3(ceil_div(w, 32), ceil_div(h, 8)), 256, 0, st>>>(d[0], d[1], d[2], h, w, d_arcs, (int)arcs.size(), (float)sqrt(0.125));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(planes[c], d[c], sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return 0;
 }

@@ -1,0 +1,202 @@
+// k8_features.cuh -- image features between stage 2 and the colour transform: k x k upsampling.
+//
+// k8_upsample replaces Frame.performUpsampling (J/frame/Frame.java:217-260): per output phase (ky, kx) a 5x5 kernel over the
+// mirrored neighbourhood, accumulated in (iy, ix) order with uncontracted multiply-adds, clamped to the window's range with
+// the Java's initial min / max (Float.MAX_VALUE / Float.MIN_VALUE -- the smallest positive float, a reference quirk kept).
+#pragma once
+#include "common.cuh"
+#include "k2_restore.cuh"
+#include "k7_blend.cuh"
+
+__device__ __forceinline__ int mirror_coord(int c, int size) {      // MathHelper.mirrorCoordinate (J/util/MathHelper.java:323-329)
+    while (c < 0 || c >= size) {
+        const int tc = ~c;
+        c = tc >= 0 ? tc : (size << 1) + tc;
+    }
+    return c;
+}
+
+// one thread per INPUT pixel: the 25 samples are loaded once and feed the k * k output phases; weights in shared memory
+__global__ void k8_upsample(const float *__restrict__ in, int h, int w, int k, const float *__restrict__ weights, float *__restrict__ out) {
+    extern __shared__ float s_w[];
+    for (int i = threadIdx.x; i < k * k * 25; i += blockDim.x) s_w[i] = weights[i];
+    __syncthreads();
+    const long long n = (long long)h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        float s[25];
+        float mn = 3.4028234663852886e38f, mx = 1.401298464324817e-45f;
+#pragma unroll
+        for (int iy = 0; iy < 5; iy++) {
+            const int yy = mirror_coord(y + iy - 2, h);
+#pragma unroll
+            for (int ix = 0; ix < 5; ix++) {
+                const int xx = mirror_coord(x + ix - 2, w);
+                const float v = in[(size_t)yy * w + xx];
+                s[iy * 5 + ix] = v;
+                if (v < mn) mn = v;
+                if (v > mx) mx = v;
+            }
+        }
+        for (int ky = 0; ky < k; ky++)
+            for (int kx = 0; kx < k; kx++) {
+                const float *wt = s_w + (ky * k + kx) * 25;
+                float total = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 25; t++) total = __fadd_rn(total, __fmul_rn(wt[t], s[t]));
+                out[(size_t)(y * k + ky) * w * k + x * k + kx] = total < mn ? mn : (total > mx ? mx : total);
+            }
+    }
+}
+
+// ---- noise: XorShiro (J/frame/features/XorShiro.java), Frame.initializeNoise / synthesizeNoise (J/frame/Frame.java:748-835) ----
+__host__ __device__ __forceinline__ unsigned long long split_mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+struct NoiseArgs {
+    float *local[3];          // uniform [1, 2) samples
+    float *plane[3];          // X, Y, B in / out
+    int h, w, group_dim, log_dim, group_cols, num_groups;
+    unsigned long long seed0;
+    float lut[8];
+    float base_x, base_b;
+};
+
+// XorShiro is eight independent xorshift128+ lanes; lane i supplies ints 2i and 2i+1 of every batch of 16.  One thread per
+// (group, lane) walks its lane through the group's 3 * rows * ceil(cols / 16) batches.
+__global__ void k8_noise_rng(NoiseArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int group = t >> 3, lane = t & 7;
+    if (group >= A.num_groups) return;
+    const int y0 = (group / A.group_cols) << A.log_dim, x0 = (group % A.group_cols) << A.log_dim;
+    const unsigned long long seed1 = ((unsigned long long)(unsigned)x0 << 32) | (unsigned long long)(unsigned)y0;
+    unsigned long long s0 = split_mix64(A.seed0 + 0x9e3779b97f4a7c15ULL), s1 = split_mix64(seed1 + 0x9e3779b97f4a7c15ULL);
+    for (int i = 0; i < lane; i++) { s0 = split_mix64(s0); s1 = split_mix64(s1); }
+    const int ys = min(A.group_dim, A.h - y0), xs = min(A.group_dim, A.w - x0);
+    for (int c = 0; c < 3; c++)
+        for (int y = 0; y < ys; y++) {
+            float *row = A.local[c] + (size_t)(y0 + y) * A.w + x0;
+            for (int x = 0; x < xs; x += 16) {
+                const unsigned long long a = s1;
+                unsigned long long b = s0;
+                const unsigned long long sum = a + b;
+                s0 = a;
+                b ^= b << 23;
+                s1 = b ^ a ^ (b >> 18) ^ (a >> 5);
+                const int p = x + 2 * lane;
+                if (p < xs) row[p] = __uint_as_float(((unsigned)(sum & 0xffffffffULL) >> 9) | 0x3f800000u);
+                if (p + 1 < xs) row[p + 1] = __uint_as_float(((unsigned)(sum >> 32) >> 9) | 0x3f800000u);
+            }
+        }
+}
+
+// Laplacian-filtered noise of the three channels at one pixel, then the intensity-dependent mix into X, Y, B
+__global__ void k8_noise_apply(NoiseArgs A) {
+    const long long n = (long long)A.h * A.w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / A.w), x = (int)(i - (long long)y * A.w);
+        float nz[3];
+        for (int c = 0; c < 3; c++) {
+            float acc = 0.0f;
+            for (int iy = 0; iy < 5; iy++) {
+                const int cy = mirror_coord(y + iy - 2, A.h);
+                for (int ix = 0; ix < 5; ix++) {
+                    const int cx = mirror_coord(x + ix - 2, A.w);
+                    const float lap = (iy == 2 && ix == 2) ? -3.84f : 0.16f;
+                    acc = __fadd_rn(acc, __fmul_rn(A.local[c][(size_t)cy * A.w + cx], lap));
+                }
+            }
+            nz[c] = acc;
+        }
+        const float X = A.plane[0][i], Y = A.plane[1][i], B = A.plane[2][i];
+        float in_r = __fadd_rn(Y, X);
+        in_r = in_r < 0.0f ? 0.0f : __fmul_rn(3.0f, in_r);
+        float in_g = __fsub_rn(Y, X);
+        in_g = in_g < 0.0f ? 0.0f : __fmul_rn(3.0f, in_g);
+        int ir, ig;
+        float fr, fg;
+        if (in_r >= 7.0f) { ir = 6; fr = 1.0f; } else { ir = (int)in_r; fr = __fsub_rn(in_r, (float)ir); }
+        if (in_g >= 7.0f) { ig = 6; fg = 1.0f; } else { ig = (int)in_g; fg = __fsub_rn(in_g, (float)ig); }
+        float sr = __fadd_rn(__fmul_rn(__fsub_rn(A.lut[ir + 1], A.lut[ir]), fr), A.lut[ir]);
+        float sg = __fadd_rn(__fmul_rn(__fsub_rn(A.lut[ig + 1], A.lut[ig]), fg), A.lut[ig]);
+        sr = clamp01(sr);
+        sg = clamp01(sg);
+        const float nr = __fmul_rn(sr, __fadd_rn(__fmul_rn(0.00171875f, nz[0]), __fmul_rn(0.21828125f, nz[2])));
+        const float ng = __fmul_rn(sg, __fadd_rn(__fmul_rn(0.00171875f, nz[1]), __fmul_rn(0.21828125f, nz[2])));
+        const float nrg = __fadd_rn(nr, ng);
+        A.plane[1][i] = __fadd_rn(Y, nrg);
+        A.plane[0][i] = __fadd_rn(X, __fsub_rn(__fadd_rn(__fmul_rn(A.base_x, nrg), nr), ng));
+        A.plane[2][i] = __fadd_rn(B, __fmul_rn(A.base_b, nrg));
+    }
+}
+
+// ---- splines: Spline.renderSpline's pixel loop (J/frame/features/spline/Spline.java:170-199) ----
+// The arcs (position, colour values, sigma, bounding box) are prepared on the host (splines_host.cuh); here every pixel walks
+// the arcs in order and adds the contributions of those whose box covers it, which is the order the Java adds them in.
+struct SplineArcDev {
+    float y, x, sigma, inv_sigma;
+    float value[3];
+    int x0, x1, y0, y1;     // inclusive box
+};
+
+__device__ __forceinline__ float erf_ref(float z) {      // MathHelper.erf (J/util/MathHelper.java:40-66): float polynomial, double exp
+    const float az = fabsf(z);
+    float r;
+    if (az > 1e-4f) {
+        const float t = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(az, 0.5f), 1.0f));
+        float u = __fsub_rn(__fmul_rn(t, 0.17087277f), 0.82215223f);
+        u = __fadd_rn(__fmul_rn(t, u), 1.48851587f);
+        u = __fsub_rn(__fmul_rn(t, u), 1.13520398f);
+        u = __fadd_rn(__fmul_rn(t, u), 0.27886807f);
+        u = __fsub_rn(__fmul_rn(t, u), 0.18628806f);
+        u = __fadd_rn(__fmul_rn(t, u), 0.09678418f);
+        u = __fadd_rn(__fmul_rn(t, u), 0.37409196f);
+        u = __fadd_rn(__fmul_rn(t, u), 1.00002368f);
+        u = __fsub_rn(__fmul_rn(t, u), 1.26551223f);
+        const float e = (float)exp((double)__fadd_rn(__fmul_rn(-z, z), u));
+        r = __fsub_rn(1.0f, __fmul_rn(t, e));
+    } else {
+        const float t = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(az, 0.47047f), 1.0f));
+        float u = __fsub_rn(__fmul_rn(t, 0.7478556f), 0.0958798f);
+        u = __fadd_rn(__fmul_rn(t, u), 0.3480242f);
+        u = __fmul_rn(t, u);
+        const float e = (float)exp((double)__fmul_rn(-z, z));
+        r = __fsub_rn(1.0f, __fmul_rn(u, e));
+    }
+    return z < 0.0f ? -r : r;
+}
+
+#define K8_ARC_CHUNK 128
+__global__ void k8_splines(float *p0, float *p1, float *p2, int h, int w, const SplineArcDev *__restrict__ arcs, int n, float sqrt_f) {
+    __shared__ SplineArcDev s_arc[K8_ARC_CHUNK];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+    const bool inside = x < w && y < h;
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    if (inside) { acc[0] = p0[(size_t)y * w + x]; acc[1] = p1[(size_t)y * w + x]; acc[2] = p2[(size_t)y * w + x]; }
+    for (int base = 0; base < n; base += K8_ARC_CHUNK) {
+        const int cnt = min(K8_ARC_CHUNK, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_arc[i] = arcs[base + i];
+        __syncthreads();
+        for (int i = 0; i < cnt; i++) {
+            const SplineArcDev &a = s_arc[i];
+            if (a.x1 < tx0 || a.x0 > tx0 + 31 || a.y1 < ty0 || a.y0 > ty0 + 7) continue;      // whole tile outside: uniform skip
+            if (!inside || x < a.x0 || x > a.x1 || y < a.y0 || y > a.y1) continue;
+            const float dy = __fsub_rn((float)y, a.y), dx = __fsub_rn((float)x, a.x);
+            const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+            const float half = __fmul_rn(0.5f, dist);
+            float factor = erf_ref(__fmul_rn(__fadd_rn(half, sqrt_f), a.inv_sigma));
+            factor = __fsub_rn(factor, erf_ref(__fmul_rn(__fsub_rn(half, sqrt_f), a.inv_sigma)));
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float extra = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(0.25f, a.value[c]), a.sigma), factor), factor);
+                acc[c] = __fadd_rn(acc[c], extra);
+            }
+        }
+    }
+    if (inside) { p0[(size_t)y * w + x] = acc[0]; p1[(size_t)y * w + x] = acc[1]; p2[(size_t)y * w + x] = acc[2]; }
+}

@@ -20,6 +20,7 @@ import numpy as np
 
 from . import frontend
 from .params import FrameParams
+from .upsampling import up_weights
 
 ENC_VARDCT, ENC_MODULAR = 0, 1
 FLAG_NOISE, FLAG_PATCHES, FLAG_SPLINES, FLAG_USE_LF_FRAME = 1, 2, 16, 32
@@ -55,6 +56,15 @@ class CudaEngine:
 
     def blend(self, op, canvas, a, b, fa, ra):
         self.rec.blend(op, canvas, a, b, fa, ra)
+
+    def upsample(self, plane, k, weights):
+        return self.rec.performUpsampling(plane, k, weights)
+
+    def noise(self, planes, group_dim, seed0, lut, base_x, base_b):
+        return self.rec.synthesizeNoise(planes, group_dim, seed0, lut, base_x, base_b)
+
+    def splines(self, planes, splines, quant_adjust, base_x, base_b):
+        return self.rec.renderSplines(planes, splines, quant_adjust, base_x, base_b)
 
     def close(self):
         self.rec.close()
@@ -258,10 +268,8 @@ class JXLDecoder:
     def decode_frame(self, parsed, k):
         """-> (list of _Buf of frame size: colour channels then extra channels, colour transform still pending?, params)."""
         info, f = parsed.info, parsed.frames[k]
-        if f["flags"] & (FLAG_NOISE | FLAG_SPLINES | FLAG_USE_LF_FRAME):
-            raise NotImplementedError("noise / splines / LF frames (flags=%d): SURVEY.md 8f-4" % f["flags"])
-        if f["upsampling"] != 1 or any(u != 1 for u in f["ec_upsampling"]):
-            raise NotImplementedError("upsampling: SURVEY.md 8f-4")
+        if f["flags"] & FLAG_USE_LF_FRAME:
+            raise NotImplementedError("frames that take their LF from an LF frame: SURVEY.md 8f-3")
         h, w = f["height"], f["width"]
         bits = info["bits_per_sample"]
         mod = None
@@ -276,7 +284,8 @@ class JXLDecoder:
             st["qm_weights"], st["qm_offsets"] = self.quant_tables(parsed, k, f)
             p = self.frame_params(info, f)
             # patches and saveBeforeCT act on the planes BEFORE the colour transform (JXLCodestreamDecoder.java:611-616)
-            pending = p.color_mode != 0 and (bool(f["flags"] & FLAG_PATCHES) or f["save_before_ct"])
+            upsampled = f["upsampling"] != 1 or any(u != 1 for u in f["ec_upsampling"])
+            pending = p.color_mode != 0 and (bool(f["flags"] & (FLAG_PATCHES | FLAG_SPLINES | FLAG_NOISE)) or f["save_before_ct"] or upsampled)
             if pending:
                 q = p.copy()
                 q.color_mode = 0
@@ -405,17 +414,48 @@ class JXLDecoder:
         reference = [None, None, None, None]
         linear = bool(info["xyb_encoded"])
         t1 = time.perf_counter()
+        visible_frames = invisible_frames = 0
         for k, f in enumerate(parsed.frames):
             if f["type"] == 1 or f["lf_level"] > 0:
                 raise NotImplementedError("LF frames: SURVEY.md 8f-3")
             bufs, pending, p = self.decode_frame(parsed, k)
             frame_colors = 3 if (info["xyb_encoded"] or f["encoding"] == ENC_VARDCT) else colors
             save = (f["save_as_reference"] != 0 or f["duration"] == 0) and not f["is_last"] and f["type"] != 1
+            if f["type"] in (0, 3) and (f["duration"] != 0 or f["is_last"]):          # Frame.isVisible
+                visible_frames, invisible_frames = visible_frames + 1, 0
+            else:
+                invisible_frames += 1
+            # Frame.upsample (:725-737): every channel by its own factor, the frame rectangle by the colour factor
+            fh, fw, fy0, fx0 = f["height"], f["width"], f["y0"], f["x0"]
+            ups = f["upsampling"]
+            for c, b in enumerate(bufs):
+                kk = ups if c < frame_colors else f["ec_upsampling"][c - frame_colors]
+                if kk > 1:
+                    b.cast_to_float(info["bits_per_sample"] if c < frame_colors else info["extra_channels"][c - frame_colors]["bits_per_sample"])
+                    b.a = self.engine.upsample(b.a, kk, up_weights(kk, info["up%d" % kk]))
+            fh, fw, fy0, fx0 = fh * ups, fw * ups, fy0 * ups, fx0 * ups
+            fr = dict(f, height=fh, width=fw, y0=fy0, x0=fx0)
+            has_noise = bool(f["flags"] & FLAG_NOISE)
             if save and f["save_before_ct"]:
                 reference[f["save_as_reference"]] = [_Buf(b.a.copy()) for b in bufs]
-            self._compute_patches(info, f, bufs, frame_colors, reference)
+            self._compute_patches(info, fr, bufs, frame_colors, reference)
+            if f["flags"] & FLAG_SPLINES and f["splines"]:
+                for c in range(3):
+                    bufs[c].cast_to_float(info["bits_per_sample"])
+                xyb = self.engine.splines(np.stack([bufs[c].a for c in range(3)]), f["splines"], f["spline_quant_adjust"], f["base_corr_x"], f["base_corr_b"])
+                for c in range(3):
+                    bufs[c].a = np.ascontiguousarray(xyb[c])
+            if has_noise:
+                for c in range(3):
+                    bufs[c].cast_to_float(info["bits_per_sample"])
+                seed0 = (visible_frames << 32) | invisible_frames
+                xyb = self.engine.noise(np.stack([bufs[c].a for c in range(3)]), f["group_dim"], seed0, f["noise"], f["base_corr_x"], f["base_corr_b"])
+                for c in range(3):
+                    bufs[c].a = np.ascontiguousarray(xyb[c])
             if pending:
-                rgb = self.engine.color(p, np.stack([bufs[c].a for c in range(3)]))
+                q = p.copy()
+                q.width, q.height = bufs[0].a.shape[1], bufs[0].a.shape[0]
+                rgb = self.engine.color(q, np.stack([bufs[c].a for c in range(3)]))
                 for c in range(3):
                     bufs[c] = _Buf(np.ascontiguousarray(rgb[c]))
             if canvas is None:
@@ -427,9 +467,9 @@ class JXLDecoder:
                     canvas = [_Buf(b.a.copy()) for b in canvas]
                 # blendFrame (:499-523)
                 ih, iw = info["height"], info["width"]
-                ps = (min(max(f["y0"], 0), ih), min(max(f["x0"], 0), iw))
-                fo = (ps[0] - f["y0"], ps[1] - f["x0"])
-                size = (min(f["y0"] + f["height"], ih) - ps[0], min(f["x0"] + f["width"], iw) - ps[1])
+                ps = (min(max(fy0, 0), ih), min(max(fx0, 0), iw))
+                fo = (ps[0] - fy0, ps[1] - fx0)
+                size = (min(fy0 + fh, ih) - ps[0], min(fx0 + fw, iw) - ps[1])
                 if size[0] > 0 and size[1] > 0:
                     for c in range(len(canvas)):
                         if c >= colors:

@@ -114,6 +114,15 @@ void describe(jxlf_image &im) {
             j.close('}');
         }
         j.close(']');
+        j.num("spline_quant_adjust", f.spline_quant_adjust);
+        j.open("splines", '[');
+        for (auto &sp : f.splines) {
+            j.open(nullptr, '{');
+            j.iarr("points", sp.points.begin(), sp.points.end());
+            j.iarr("coeff", &sp.coeff[0][0], &sp.coeff[0][0] + 128);
+            j.close('}');
+        }
+        j.close(']');
         j.open("ec_blending", '[');
         for (auto &b : h.ec_blending) {
             j.open(nullptr, '[');

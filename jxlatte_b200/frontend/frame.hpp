@@ -49,6 +49,10 @@ struct FrameData {
     float noise[8] = {0};
     int num_patches = 0, num_splines = 0;
     std::vector<PatchInfo> patches;
+    // SplinesBundle (J/frame/features/spline/SplinesBundle.java:25-75): control points (x, y) and 4 x 32 coefficients per spline
+    struct SplineInfo { std::vector<int32_t> points; int32_t coeff[4][32]; };
+    std::vector<SplineInfo> splines;
+    int32_t spline_quant_adjust = 0;
     // VarDCT state, frame level
     std::vector<int32_t> qcoeff[3];
     std::vector<float> lf[3];
@@ -235,12 +239,39 @@ class FrameDecoder {
             if (ih_.color_channels() < 3) throw StreamError("splines in a greyscale image");
             EntropyStream es(br, 6);
             f.num_splines = 1 + (int)es.read(br, 2);
-            for (int i = 0; i < f.num_splines; i++) { es.read(br, 1); es.read(br, 1); }
-            es.read(br, 0);
+            f.splines.resize(f.num_splines);
+            std::vector<int32_t> start(2 * (size_t)f.num_splines);
             for (int i = 0; i < f.num_splines; i++) {
+                int32_t x = (int32_t)es.read(br, 1), y = (int32_t)es.read(br, 1);
+                if (i) {
+                    x = detail::wrap_add(unpack_signed((uint32_t)x), start[2 * i - 2]);
+                    y = detail::wrap_add(unpack_signed((uint32_t)y), start[2 * i - 1]);
+                }
+                start[2 * i] = x;
+                start[2 * i + 1] = y;
+            }
+            f.spline_quant_adjust = unpack_signed(es.read(br, 0));
+            for (int i = 0; i < f.num_splines; i++) {
+                FrameData::SplineInfo &sp = f.splines[i];
                 const uint32_t points = 1 + es.read(br, 3);
-                for (uint32_t j = 1; j < points; j++) { es.read(br, 4); es.read(br, 4); }
-                for (int j = 0; j < 4 * 32; j++) es.read(br, 5);
+                if (points > (1u << 20)) throw StreamError("too many spline control points");
+                std::vector<int32_t> dx(points - 1), dy(points - 1);
+                for (uint32_t j = 0; j + 1 < points; j++) {
+                    dx[j] = unpack_signed(es.read(br, 4));
+                    dy[j] = unpack_signed(es.read(br, 4));
+                }
+                int32_t cx = start[2 * i], cy = start[2 * i + 1], ddx = 0, ddy = 0;
+                sp.points = {cx, cy};
+                for (uint32_t j = 1; j < points; j++) {
+                    ddy = detail::wrap_add(ddy, dy[j - 1]);
+                    ddx = detail::wrap_add(ddx, dx[j - 1]);
+                    cy = detail::wrap_add(cy, ddy);
+                    cx = detail::wrap_add(cx, ddx);
+                    sp.points.push_back(cx);
+                    sp.points.push_back(cy);
+                }
+                for (int k = 0; k < 4; k++)                      // X, Y, B, sigma
+                    for (int j = 0; j < 32; j++) sp.coeff[k][j] = unpack_signed(es.read(br, 5));
             }
             es.expect_final_state("splines");
         }

@@ -220,6 +220,38 @@ class Reconstructor:
         self._check(self._L.jxlb200_restore_dev(self._h, C.byref(p), C.byref(slab) if slab is not None else None,
                                                 _lib.planes(xyb), int(pitch), hm, sh, _lib.planes(out)))
 
+    # -- upsampling (Frame.performUpsampling) --
+    def performUpsampling(self, plane, k, weights):
+        """One float32 channel h x w -> (h*k) x (w*k); weights float32 [k][k][5][5] (jxlatte_b200.upsampling.up_weights)."""
+        a, wt = _c(plane, np.float32), _c(weights, np.float32)
+        if a.ndim != 2 or wt.shape != (k, k, 5, 5):
+            raise ValueError("plane must be 2-D and weights [k][k][5][5]")
+        out = np.empty((a.shape[0] * k, a.shape[1] * k), np.float32)
+        self._check(self._L.jxlb200_upsample(self._h, _ptr(a), a.shape[0], a.shape[1], int(k), _ptr(wt), _ptr(out)))
+        return out
+
+    # -- noise (Frame.initializeNoise + synthesizeNoise) --
+    def synthesizeNoise(self, planes, group_dim, seed0, lut, base_corr_x, base_corr_b):
+        """X, Y, B planes [3, h, w] -> planes with the frame's noise added."""
+        buf = [np.array(planes[c], dtype=np.float32, order="C", copy=True) for c in range(3)]
+        lt = _c(lut, np.float32)
+        h, w = buf[0].shape
+        self._check(self._L.jxlb200_noise(self._h, _lib.planes([_ptr(a) for a in buf]), h, w, int(group_dim), int(seed0),
+                                          _ptr(lt), float(base_corr_x), float(base_corr_b)))
+        return np.stack(buf)
+
+    # -- splines (Frame.renderSplines) --
+    def renderSplines(self, planes, splines, quant_adjust, base_corr_x, base_corr_b):
+        """X, Y, B planes [3, h, w] -> planes with the splines drawn.  splines: [{"points": [x0, y0, ...], "coeff": 128 ints}]."""
+        buf = [np.array(planes[c], dtype=np.float32, order="C", copy=True) for c in range(3)]
+        h, w = buf[0].shape
+        npts = np.array([len(s["points"]) // 2 for s in splines], np.int32)
+        pts = np.array([v for s in splines for v in s["points"]], np.int32)
+        cf = np.array([v for s in splines for v in s["coeff"]], np.int32)
+        self._check(self._L.jxlb200_splines(self._h, _lib.planes([_ptr(a) for a in buf]), h, w, len(splines), _ptr(npts), _ptr(pts),
+                                            _ptr(cf), int(quant_adjust), float(base_corr_x), float(base_corr_b)))
+        return np.stack(buf)
+
     # -- blending (JXLCodestreamDecoder.blendAdd / blendMult / blendBlend / blendMulAdd) --
     def blend(self, op, canvas, a, b, fa=None, ra=None):
         """One rectangle of one channel; op = dict(mode, is_int, is_alpha, has_extra, clamp, premult); canvas, a (the Java's

@@ -95,6 +95,11 @@ void orc_invert_subsampling(const orc_frame_params *p, const float *const in[3],
 int32_t orc_blend(int32_t mode, int32_t is_int, int32_t is_alpha, int32_t has_extra, int32_t clamp, int32_t premult,
     int32_t h, int32_t w, void *canvas, int64_t cp, const void *a, int64_t ap, const void *b, int64_t bp,
     const float *fa, int64_t fap, const float *ra, int64_t rap);
+void orc_upsample(const float *in, int32_t h, int32_t w, int32_t k, const float *weights, float *out);
+void orc_noise(float *const planes[3], int32_t h, int32_t w, int32_t group_dim, int64_t seed0, const float *lut,
+    float base_x, float base_b);
+int32_t orc_splines(float *const planes[3], int32_t h, int32_t w, int32_t num_splines, const int32_t *npoints, const int32_t *points,
+    const int32_t *coeff, int32_t quant_adjust, float base_x, float base_b);
 int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,

@@ -331,3 +331,45 @@ def blend(op, canvas, a, b, fa=None, ra=None):
                      cp, cpi, ap, api, bp, bpi, fp, fpi, rp, rpi)
     if rc:
         raise RuntimeError("orc_blend rc=%d" % rc)
+
+
+def upsample(plane, k, weights):
+    """Frame.performUpsampling on one float32 channel; weights float32 [k][k][5][5]."""
+    L = lib()
+    a = _c(plane, np.float32)
+    wt = _c(weights, np.float32)
+    h, w = a.shape
+    out = np.zeros((h * k, w * k), np.float32)
+    L.orc_upsample.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.orc_upsample.restype = None
+    L.orc_upsample(a.ctypes.data, h, w, int(k), wt.ctypes.data, out.ctypes.data)
+    return out
+
+
+def noise(planes, group_dim, seed0, lut, base_x, base_b):
+    """Frame.initializeNoise + synthesizeNoise on X, Y, B planes [3, h, w]; returns the new planes."""
+    L = lib()
+    buf = [np.array(planes[c], dtype=np.float32, order="C", copy=True) for c in range(3)]
+    h, w = buf[0].shape
+    lt = _c(lut, np.float32)
+    L.orc_noise.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_float, C.c_float]
+    L.orc_noise.restype = None
+    L.orc_noise(_planes(buf, C.c_float), h, w, int(group_dim), int(seed0), lt.ctypes.data, float(base_x), float(base_b))
+    return np.stack(buf)
+
+
+def splines(planes, splines_list, quant_adjust, base_x, base_b):
+    """Frame.renderSplines on X, Y, B planes [3, h, w]; splines_list: [{"points": [x0, y0, x1, y1, ...], "coeff": 128 ints}]."""
+    L = lib()
+    buf = [np.array(planes[c], dtype=np.float32, order="C", copy=True) for c in range(3)]
+    h, w = buf[0].shape
+    npts = np.array([len(s["points"]) // 2 for s in splines_list], np.int32)
+    pts = np.array([v for s in splines_list for v in s["points"]], np.int32)
+    cf = np.array([v for s in splines_list for v in s["coeff"]], np.int32)
+    L.orc_splines.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float]
+    L.orc_splines.restype = C.c_int32
+    rc = L.orc_splines(_planes(buf, C.c_float), h, w, len(splines_list), npts.ctypes.data, pts.ctypes.data, cf.ctypes.data,
+                       int(quant_adjust), float(base_x), float(base_b))
+    if rc:
+        raise RuntimeError("orc_splines rc=%d" % rc)
+    return np.stack(buf)

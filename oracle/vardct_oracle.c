@@ -1305,3 +1305,310 @@ int32_t orc_blend(int32_t mode, int32_t is_int, int32_t is_alpha, int32_t has_ex
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame.performUpsampling  (J/frame/Frame.java:217-260): k x k upsampling of one float channel with the per-phase 5x5
+ * kernels weights[ky][kx][iy][ix] (ImageHeader.getUpWeights), mirrored edges, result clamped to the [min, max] of the 25
+ * samples -- with the Java's initial values (min = Float.MAX_VALUE, max = Float.MIN_VALUE, the smallest POSITIVE float).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_upsample(const float *in, int32_t h, int32_t w, int32_t k, const float *weights, float *out) {
+    for (int y = 0; y < h; y++) {
+        for (int ky = 0; ky < k; ky++) {
+            for (int x = 0; x < w; x++) {
+                for (int kx = 0; kx < k; kx++) {
+                    const float *wt = weights + (size_t)(ky * k + kx) * 25;
+                    float total = 0.0f;
+                    float min = 3.4028234663852886e38f;
+                    float max = 1.401298464324817e-45f;
+                    for (int iy = 0; iy < 5; iy++) {
+                        for (int ix = 0; ix < 5; ix++) {
+                            int newY = orc_mirror_coordinate(y + iy - 2, h);
+                            int newX = orc_mirror_coordinate(x + ix - 2, w);
+                            float sample = in[(size_t)newY * w + newX];
+                            if (sample < min) min = sample;
+                            if (sample > max) max = sample;
+                            total += wt[iy * 5 + ix] * sample;
+                        }
+                    }
+                    out[(size_t)(y * k + ky) * w * k + x * k + kx] = total < min ? min : total > max ? max : total;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Noise: XorShiro (J/frame/features/XorShiro.java), Frame.initializeNoise / synthesizeNoise (J/frame/Frame.java:748-835)
+ * ---------------------------------------------------------------------------------------------- */
+static uint64_t split_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+typedef struct { uint64_t state0[8], state1[8]; uint32_t batch[16]; int batchPos; } xorshiro_t;
+static void xs_init(xorshiro_t *r, uint64_t seed0, uint64_t seed1) {
+    r->state0[0] = split_mix64(seed0 + 0x9e3779b97f4a7c15ULL);
+    r->state1[0] = split_mix64(seed1 + 0x9e3779b97f4a7c15ULL);
+    for (int i = 1; i < 8; i++) {
+        r->state0[i] = split_mix64(r->state0[i - 1]);
+        r->state1[i] = split_mix64(r->state1[i - 1]);
+    }
+    r->batchPos = 16;
+}
+static void xs_fill_batch(xorshiro_t *r) {
+    for (int i = 0; i < 8; i++) {
+        const uint64_t a = r->state1[i];
+        uint64_t b = r->state0[i];
+        const uint64_t c = a + b;
+        r->state0[i] = a;
+        b ^= b << 23;
+        r->state1[i] = b ^ a ^ (b >> 18) ^ (a >> 5);
+        r->batch[2 * i] = (uint32_t)(c & 0xffffffffULL);
+        r->batch[2 * i + 1] = (uint32_t)(c >> 32);
+    }
+    r->batchPos = 0;
+}
+static void xs_fill(xorshiro_t *r, uint32_t *bits, int n) {
+    for (int i = 0; i < n; i++) {
+        if (r->batchPos >= 16) xs_fill_batch(r);
+        bits[i] = r->batch[r->batchPos++];
+    }
+}
+
+/* planes[3]: X, Y, B of the (upsampled) frame, h x w, modified in place.  seed0 = (visibleFrames << 32) | invisibleFrames. */
+void orc_noise(float *const planes[3], int32_t h, int32_t w, int32_t group_dim, int64_t seed0, const float *lut,
+    float base_x, float base_b) {
+    static const float laplacian[5][5] = {
+        {0.16f, 0.16f, 0.16f, 0.16f, 0.16f}, {0.16f, 0.16f, 0.16f, 0.16f, 0.16f}, {0.16f, 0.16f, -3.84f, 0.16f, 0.16f},
+        {0.16f, 0.16f, 0.16f, 0.16f, 0.16f}, {0.16f, 0.16f, 0.16f, 0.16f, 0.16f}};
+    const size_t n = (size_t)h * w;
+    float *local[3], *noise[3];
+    for (int c = 0; c < 3; c++) { local[c] = (float *)calloc(n, sizeof(float)); noise[c] = (float *)calloc(n, sizeof(float)); }
+    const int log_dim = group_dim == 128 ? 7 : group_dim == 256 ? 8 : group_dim == 512 ? 9 : 10;
+    const int groupRowStride = (w + group_dim - 1) / group_dim;
+    const int numGroups = groupRowStride * ((h + group_dim - 1) / group_dim);
+    for (int group = 0; group < numGroups; group++) {
+        int y0 = (group / groupRowStride) << log_dim;
+        int x0 = (group % groupRowStride) << log_dim;
+        uint64_t seed1 = (((uint64_t)(uint32_t)x0) << 32) | (uint64_t)(uint32_t)y0;
+        int ySize = group_dim < h - y0 ? group_dim : h - y0;
+        int xSize = group_dim < w - x0 ? group_dim : w - x0;
+        xorshiro_t rng;
+        xs_init(&rng, (uint64_t)seed0, seed1);
+        uint32_t bits[16];
+        for (int c = 0; c < 3; c++)
+            for (int y = 0; y < ySize; y++)
+                for (int x = 0; x < xSize; x += 16) {
+                    xs_fill(&rng, bits, 16);
+                    for (int i = 0; i < 16 && x + i < xSize; i++) {
+                        uint32_t f = (bits[i] >> 9) | 0x3f800000u;
+                        float v;
+                        memcpy(&v, &f, 4);
+                        local[c][(size_t)(y0 + y) * w + x0 + x + i] = v;
+                    }
+                }
+    }
+    for (int c = 0; c < 3; c++)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                float acc = 0.0f;
+                for (int iy = 0; iy < 5; iy++)
+                    for (int ix = 0; ix < 5; ix++) {
+                        int cy = orc_mirror_coordinate(y + iy - 2, h);
+                        int cx = orc_mirror_coordinate(x + ix - 2, w);
+                        acc += local[c][(size_t)cy * w + cx] * laplacian[iy][ix];
+                    }
+                noise[c][(size_t)y * w + x] = acc;
+            }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const size_t i = (size_t)y * w + x;
+            float inScaledR = planes[1][i] + planes[0][i];
+            inScaledR = inScaledR < 0.0f ? 0.0f : 3.0f * inScaledR;
+            float inScaledG = planes[1][i] - planes[0][i];
+            inScaledG = inScaledG < 0.0f ? 0.0f : 3.0f * inScaledG;
+            int intInR, intInG;
+            float fracInR, fracInG;
+            if (inScaledR >= 7.0f) { intInR = 6; fracInR = 1.0f; } else { intInR = (int)inScaledR; fracInR = inScaledR - intInR; }
+            if (inScaledG >= 7.0f) { intInG = 6; fracInG = 1.0f; } else { intInG = (int)inScaledG; fracInG = inScaledG - intInG; }
+            float sr = (lut[intInR + 1] - lut[intInR]) * fracInR + lut[intInR];
+            float sg = (lut[intInG + 1] - lut[intInG]) * fracInG + lut[intInG];
+            sr = clamp_asc(sr, 0.0f, 1.0f);
+            sg = clamp_asc(sg, 0.0f, 1.0f);
+            float nr = sr * (0.00171875f * noise[0][i] + 0.21828125f * noise[2][i]);
+            float ng = sg * (0.00171875f * noise[1][i] + 0.21828125f * noise[2][i]);
+            float nrg = nr + ng;
+            planes[1][i] += nrg;
+            planes[0][i] += base_x * nrg + nr - ng;
+            planes[2][i] += base_b * nrg;
+        }
+    for (int c = 0; c < 3; c++) { free(local[c]); free(noise[c]); }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Splines  (J/frame/features/spline/Spline.java, J/frame/Frame.java:739-746, MathHelper.erf :40-66)
+ * Quirks kept: Spline's constructor drops its splineID, so every spline is drawn with spline 0's coefficients (:22-24,
+ * :141); MathHelper.max returns the MINIMUM of its arguments (J/util/MathHelper.java:190-195).
+ * ---------------------------------------------------------------------------------------------- */
+static float orc_erf(float z) {
+    const float az = fabsf(z);
+    float absErf;
+    if (az > 1e-4f) {
+        const float t = 1.0f / (az * 0.5f + 1.0f);
+        const float u = t * (t * (t * (t * (t * (t * (t * (t * (t * 0.17087277f - 0.82215223f) + 1.48851587f) - 1.13520398f)
+                          + 0.27886807f) - 0.18628806f) + 0.09678418f) + 0.37409196f) + 1.00002368f) - 1.26551223f;
+        absErf = 1.0f - t * (float)exp(-z * z + u);
+    } else {
+        const float t = 1.0f / (az * 0.47047f + 1.0f);
+        const float u = t * (t * (t * 0.7478556f - 0.0958798f) + 0.3480242f);
+        absErf = 1.0f - u * (float)exp(-z * z);
+    }
+    if (z < 0) return -absErf;
+    return absErf;
+}
+static int java_f2i(float v) { if (v != v) return 0; if (v >= 2147483648.0f) return 2147483647; if (v <= -2147483648.0f) return -2147483647 - 1; return (int)v; }
+static float fourier_ict(const float *coeffs, float t) {
+    const float SQRT_H = (float)sqrt(0.5);
+    float total = SQRT_H * coeffs[0];
+    for (int i = 1; i < 32; i++) total += coeffs[i] * (float)cos(i * (M_PI / 32.0) * (t + 0.5));
+    return total;
+}
+typedef struct { float locationY, locationX, arcLength; } arc_t;
+
+/* points: (x, y) pairs of all splines back to back, npoints[s] pairs each; coeff: [num_splines][4][32] = X, Y, B, sigma */
+int32_t orc_splines(float *const planes[3], int32_t h, int32_t w, int32_t num_splines, const int32_t *npoints, const int32_t *points,
+    const int32_t *coeff, int32_t quant_adjust, float base_x, float base_b) {
+    const float SQRT_F = (float)sqrt(0.125);
+    const int32_t *pts = points;
+    for (int s = 0; s < num_splines; s++) {
+        const int n = npoints[s];
+        /* computeCoeffs(splineID = 0) */
+        float coeffX[32], coeffY[32], coeffB[32], coeffSigma[32];
+        {
+            const int32_t *c0 = coeff; /* spline 0 */
+            float quantAdjust = quant_adjust / 8.0f;
+            float invQa = quantAdjust >= 0 ? 1.0f / (1.0f + quantAdjust) : 1.0f - quantAdjust;
+            float yAdjust = 0.106066017f * invQa, xAdjust = 0.005939697f * invQa, bAdjust = 0.098994949f * invQa, sigmaAdjust = 0.47135738f * invQa;
+            for (int i = 0; i < 32; i++) {
+                coeffY[i] = c0[32 + i] * yAdjust;
+                coeffX[i] = c0[i] * xAdjust + base_x * coeffY[i];
+                coeffB[i] = c0[64 + i] * bAdjust + base_b * coeffY[i];
+                coeffSigma[i] = c0[96 + i] * sigmaAdjust;
+            }
+        }
+        /* upsampleControlPoints */
+        int nup;
+        float *upY, *upX;
+        if (n == 1) {
+            nup = 1;
+            upY = (float *)malloc(sizeof(float)); upX = (float *)malloc(sizeof(float));
+            upY[0] = (float)pts[1]; upX[0] = (float)pts[0];
+        } else {
+            const int ne = n + 2;
+            int *ey = (int *)malloc(sizeof(int) * ne), *ex = (int *)malloc(sizeof(int) * ne);
+            ey[0] = pts[1] * 2 - pts[3]; ex[0] = pts[0] * 2 - pts[2];
+            for (int i = 0; i < n; i++) { ey[i + 1] = pts[2 * i + 1]; ex[i + 1] = pts[2 * i]; }
+            ey[ne - 1] = pts[2 * (n - 1) + 1] * 2 - pts[2 * (n - 2) + 1];
+            ex[ne - 1] = pts[2 * (n - 1)] * 2 - pts[2 * (n - 2)];
+            nup = 16 * (ne - 3) + 1;
+            upY = (float *)malloc(sizeof(float) * nup); upX = (float *)malloc(sizeof(float) * nup);
+            float t[4], pY[4], pX[4], dY[3], dX[3], aY[3], aX[3], bY[2], bX[2];
+            for (int i = 0; i < ne - 3; i++) {
+                for (int k = 0; k < 4; k++) { pY[k] = (float)ey[i + k]; pX[k] = (float)ex[i + k]; }
+                upY[i << 4] = pY[1];
+                upX[i << 4] = pX[1];
+                t[0] = 0.0f;
+                for (int k = 0; k < 3; k++) {
+                    dY[k] = pY[k + 1] - pY[k];
+                    dX[k] = pX[k + 1] - pX[k];
+                    t[k + 1] = t[k] + (float)pow(dY[k] * dY[k] + dX[k] * dX[k], 0.25);
+                }
+                for (int step = 1; step < 16; step++) {
+                    float knot = t[1] + 0.0625f * step * (t[2] - t[1]);
+                    for (int k = 0; k < 3; k++) {
+                        float f = (knot - t[k]) / (t[k + 1] - t[k]);
+                        aY[k] = dY[k] * f + pY[k];
+                        aX[k] = dX[k] * f + pX[k];
+                    }
+                    for (int k = 0; k < 2; k++) {
+                        float f = (knot - t[k]) / (t[k + 2] - t[k]);
+                        bY[k] = (aY[k + 1] - aY[k]) * f + aY[k];
+                        bX[k] = (aX[k + 1] - aX[k]) * f + aX[k];
+                    }
+                    float f = (knot - t[1]) / (t[2] - t[1]);
+                    upY[i * 16 + step] = (bY[1] - bY[0]) * f + bY[0];
+                    upX[i * 16 + step] = (bX[1] - bX[0]) * f + bX[0];
+                }
+            }
+            upY[nup - 1] = (float)pts[2 * (n - 1) + 1];
+            upX[nup - 1] = (float)pts[2 * (n - 1)];
+            free(ey); free(ex);
+        }
+        /* computeIntermediarySamples(renderDistance = 1) */
+        const float renderDistance = 1.0f;
+        int cap = 1024, narcs = 0;
+        arc_t *arcs = (arc_t *)malloc(sizeof(arc_t) * cap);
+#define PUSH(y_, x_, l_) do { if (narcs == cap) { cap *= 2; arcs = (arc_t *)realloc(arcs, sizeof(arc_t) * cap); } \
+        arcs[narcs].locationY = (y_); arcs[narcs].locationX = (x_); arcs[narcs].arcLength = (l_); narcs++; } while (0)
+        float currentY = upY[0], currentX = upX[0];
+        int nextID = 0;
+        PUSH(currentY, currentX, renderDistance);
+        while (nextID < nup) {
+            float prevY = currentY, prevX = currentX, arcLengthFromPrevious = 0.0f;
+            while (1) {
+                if (nextID >= nup) { PUSH(prevY, prevX, arcLengthFromPrevious); break; }
+                float nextY = upY[nextID], nextX = upX[nextID];
+                float dY = nextY - prevY, dX = nextX - prevX;
+                float arcLengthToNext = (float)sqrt(dY * dY + dX * dX);
+                if (arcLengthFromPrevious + arcLengthToNext >= renderDistance) {
+                    float f = (renderDistance - arcLengthFromPrevious) / arcLengthToNext;
+                    currentY = dY * f + prevY;
+                    currentX = dX * f + prevX;
+                    PUSH(currentY, currentX, renderDistance);
+                    break;
+                }
+                arcLengthFromPrevious += arcLengthToNext;
+                prevY = nextY;
+                prevX = nextX;
+                nextID++;
+            }
+        }
+#undef PUSH
+        free(upY); free(upX);
+        /* renderSpline */
+        float arcLength = (narcs - 2.0f) * renderDistance + arcs[narcs - 1].arcLength;
+        if (!(arcLength <= 0.0)) {
+            for (int i = 0; i < narcs; i++) {
+                arc_t arc = arcs[i];
+                float progressAlongArc = fminf(1.0f, i * renderDistance / arcLength);
+                float t = 31.0f * progressAlongArc;
+                float values[3];
+                values[0] = fourier_ict(coeffX, t) * arc.arcLength;
+                values[1] = fourier_ict(coeffY, t) * arc.arcLength;
+                values[2] = fourier_ict(coeffB, t) * arc.arcLength;
+                float sigma = fourier_ict(coeffSigma, t);
+                float inverseSigma = 1.0f / sigma;
+                float maxColor = 0.01f; /* MathHelper.max(...) is a minimum */
+                for (int c = 0; c < 3; c++) maxColor = values[c] < maxColor ? values[c] : maxColor;
+                float maxDist = (float)sqrt(-2.0f * sigma * sigma * ((float)log(0.1) * 3.0f - maxColor));
+                int xBegin = java_f2i(arc.locationX - maxDist + 0.5f); if (xBegin < 0) xBegin = 0;
+                int xEnd = java_f2i(arc.locationX + maxDist + 0.5f); if (xEnd > w - 1) xEnd = w - 1;
+                int yBegin = java_f2i(arc.locationY - maxDist + 0.5f); if (yBegin < 0) yBegin = 0;
+                int yEnd = java_f2i(arc.locationY + maxDist + 0.5f); if (yEnd > h - 1) yEnd = h - 1;
+                for (int c = 0; c < 3; c++)
+                    for (int y = yBegin; y <= yEnd; y++)
+                        for (int x = xBegin; x <= xEnd; x++) {
+                            float dY = y - arc.locationY, dX = x - arc.locationX;
+                            float distance = (float)sqrt(dY * dY + dX * dX);
+                            float factor = orc_erf((0.5f * distance + SQRT_F) * inverseSigma);
+                            factor -= orc_erf((0.5f * distance - SQRT_F) * inverseSigma);
+                            float extra = 0.25f * values[c] * sigma * factor * factor;
+                            planes[c][(size_t)y * w + x] += extra;
+                        }
+            }
+        }
+        free(arcs);
+        pts += 2 * n;
+    }
+    return 0;
+}

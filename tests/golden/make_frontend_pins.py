@@ -20,7 +20,7 @@ def dg(a):
 
 
 pins = {}
-for name in ("lenna", "bbb", "white", "bench", "quilt", "art", "patches-lossless", "blendmodes_5"):
+for name in ("lenna", "bbb", "white", "bench", "quilt", "art", "patches-lossless", "blendmodes_5", "wb-rainbow"):
     path = os.path.join(HERE, "samples", name + ".jxl")
     p = frontend.parse_file(path)
     i, f = p.info, p.frames[-1]

@@ -53,5 +53,14 @@ class OracleEngine:
     def blend(self, op, canvas, a, b, fa, ra):
         orc.blend(op, canvas, a, b, fa, ra)
 
+    def upsample(self, plane, k, weights):
+        return orc.upsample(plane, k, weights)
+
+    def noise(self, planes, group_dim, seed0, lut, base_x, base_b):
+        return orc.noise(planes, group_dim, seed0, lut, base_x, base_b)
+
+    def splines(self, planes, splines, quant_adjust, base_x, base_b):
+        return orc.splines(planes, splines, quant_adjust, base_x, base_b)
+
     def close(self):
         pass

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libjxlfront.so")
 SRC_DIR = os.path.join(_HERE, "frontend")
 CXX = "/usr/bin/g++"
-CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wall"]
+CXXFLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp", "-Wall"]
 
 
 class InvalidBitstreamError(IOError):

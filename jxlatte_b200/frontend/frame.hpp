@@ -392,7 +392,10 @@ class FrameDecoder {
         }
         lfg_.assign(f.num_lf_groups, LFGroupState());
         const int lf_dim = h.group_dim << 3;
-        for (int g = 0; g < f.num_lf_groups; g++) {
+        for (int idx : lf_channels) f.modular.channels[idx].allocate();
+        // LF groups are independent sections writing disjoint rectangles: one task each (the reference decodes them one
+        // after the other on the caller's thread)
+        parallel_sections(f.num_lf_groups, [&](int g) {
             BitReader &br = section(1 + g);
             const int gy = g / f.lf_group_cols, gx = g % f.lf_group_cols;
             LFGroupState &st = lfg_[g];
@@ -404,7 +407,35 @@ class FrameDecoder {
             ms.decode_channels(br);
             paste_channels(f, lf_channels, ms);
             if (h.encoding == ENC_VARDCT) read_hf_metadata(f, br, g, st);
+        });
+    }
+
+    // Runs body(0..n-1); in parallel when the frame has one TOC section per task (a single-section frame shares one reader).
+    // The first exception is re-thrown on the calling thread, invalid-stream errors before anything else.
+    template <class Body> void parallel_sections(int n, Body body) {
+        if (sections_.size() <= 1 || n <= 1) {
+            for (int i = 0; i < n; i++) body(i);
+            return;
         }
+        std::string stream_err, unsupported_err, other_err;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int i = 0; i < n; i++) {
+            try {
+                body(i);
+            } catch (const Unsupported &e) {
+#pragma omp critical(jxlf_err)
+                if (unsupported_err.empty()) unsupported_err = e.what();
+            } catch (const StreamError &e) {
+#pragma omp critical(jxlf_err)
+                if (stream_err.empty()) stream_err = e.what();
+            } catch (const std::exception &e) {
+#pragma omp critical(jxlf_err)
+                if (other_err.empty()) other_err = e.what();
+            }
+        }
+        if (!stream_err.empty()) throw StreamError(stream_err);
+        if (!unsupported_err.empty()) throw Unsupported(unsupported_err);
+        if (!other_err.empty()) throw std::runtime_error(other_err);
     }
 
     // LFCoefficients.java:20-98 (dequant, LF chroma-from-luma, adaptive smoothing) and :100-194
@@ -711,15 +742,18 @@ class FrameDecoder {
     // ---- pass groups (Frame.java:317-374, PassGroup.java:67-84) ----
     void decode_pass_groups(FrameData &f) {
         const FrameHeader &h = f.hdr;
-        for (int p = 0; p < h.num_passes; p++)
-            for (int g = 0; g < f.num_groups; g++) {
+        for (int b = 0; b < 13; b++) natural_order(b);       // fill the shared cache before any task reads it
+        for (int p = 0; p < h.num_passes; p++) {               // passes add into the same coefficients: one after the other
+            for (int idx : passes_[p].replaced) f.modular.channels[idx].allocate();
+            parallel_sections(f.num_groups, [&](int g) {
                 BitReader &br = section(2 + f.num_lf_groups + (size_t)p * f.num_groups + g);
                 if (h.encoding == ENC_VARDCT) read_hf_coefficients(f, br, p, g);
                 ModularStream ms;
                 ms.init(br, fc_, 18 + 3 * f.num_lf_groups + f.num_groups * p + g, cut_channels(f, passes_[p].replaced, g, h.group_dim));
                 ms.decode_channels(br);
                 paste_channels(f, passes_[p].replaced, ms);
-            }
+            });
+        }
     }
 
     // HFCoefficients.java:49-138 (+ context helpers :230-265).  Passes are summed into f.qcoeff (PassGroup.java:174-200).

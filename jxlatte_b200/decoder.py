@@ -34,9 +34,13 @@ class CudaEngine:
         from . import host
         self._host = host
         self.rec = host.Reconstructor(device)
+        self._qm_default = None
+        self._uploaded = None
 
     def qm_default(self):
-        return self._host.qm_generate()
+        if self._qm_default is None:        # HFGlobal.defaultParams tables: built once, shared by every frame that uses them
+            self._qm_default = self._host.qm_generate()
+        return self._qm_default
 
     def qm_generate(self, prm):
         return self._host.qm_generate(prm)
@@ -45,7 +49,9 @@ class CudaEngine:
         return self._host.qm_default_params()
 
     def reconstruct(self, p, st):
-        self.rec.setWeights(st["qm_weights"], st["qm_offsets"])
+        if st["qm_weights"] is not self._uploaded:      # same table object as the previous frame: already on the device
+            self.rec.setWeights(st["qm_weights"], st["qm_offsets"])
+            self._uploaded = st["qm_weights"]
         return self.rec.reconstruct(p, st)
 
     def modular(self, channels, transforms, bit_depth):

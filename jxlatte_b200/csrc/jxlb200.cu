@@ -706,14 +706,29 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
         for (int c = 0; c < 3; c++)      // the LF planes are 1/64 of the coefficients: whole, up front
             CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * nb, cudaMemcpyHostToDevice, up));
     }
-    const int nslab = ceil_div(H, JXLB200_PIPE_ROWS);
+    // slab schedule: one group row (256) first and last so the pipeline fills and drains quickly, JXLB200_PIPE_ROWS in between
+    std::vector<int> slab_start;
+    {
+        int y = 0;
+        const int edge = H > 2 * JXLB200_PIPE_ROWS ? 256 : JXLB200_PIPE_ROWS;
+        while (y < H) {
+            slab_start.push_back(y);
+            const int left = H - y;
+            int take = (y == 0) ? edge : JXLB200_PIPE_ROWS;
+            if (left - take < edge && left > edge && edge < JXLB200_PIPE_ROWS) take = left - edge > 0 ? ((left - edge + 255) / 256) * 256 : left;
+            if (take <= 0 || take > left) take = left;
+            if (left - take > 0 && left - take < 8) take = left;
+            y += take;
+        }
+    }
+    const int nslab = (int)slab_start.size();
     std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);
     for (int i = 0; i < nslab; i++) {
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], cudaEventDisableTiming));
     }
-    auto slab_y0 = [&](int i) { return i * JXLB200_PIPE_ROWS; };
-    auto slab_rows = [&](int i) { return std::min(JXLB200_PIPE_ROWS, H - i * JXLB200_PIPE_ROWS); };
+    auto slab_y0 = [&](int i) { return slab_start[i]; };
+    auto slab_rows = [&](int i) { return (i + 1 < nslab ? slab_start[i + 1] : H) - slab_start[i]; };
     rc = 0;
     for (int i = 0; i <= nslab && !rc; i++) {
         if (i < nslab) {

@@ -1098,4 +1098,32 @@ int32_t jxlb200_splines(jxlb200_ctx *ctx, float *const planes[3], int32_t h, int
     return 0;
 }
 
+
+// ---- PNG-ready samples from host planes (k8_pack_samples) ----
+int32_t jxlb200_pack_samples(jxlb200_ctx *ctx, const void *const planes[], const int32_t is_int[], const int32_t depth[],
+    int32_t n_channels, int32_t n_color, int32_t linear, int32_t h, int32_t w, int32_t bits, uint8_t *out) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!planes || !is_int || !depth || !out || n_channels < 1 || n_channels > 8 || h <= 0 || w <= 0) return ctx->fail(JXLB200_E_ARG, "bad arguments");
+    if (bits != 8 && bits != 16) return ctx->fail(JXLB200_E_ARG, "PNG only supports 8 and 16 (PNGWriter.java:57-58)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)h * w, obytes = n * n_channels * (bits > 8 ? 2 : 1);
+    CUDA_TRY(ctx, ctx->blend.ensure(4 * n * n_channels + obytes + 64));
+    PackArgs A;
+    cudaStream_t st = ctx->stream;
+    for (int c = 0; c < n_channels; c++) {
+        if (!planes[c] || depth[c] < 1 || depth[c] > 31) return ctx->fail(JXLB200_E_ARG, "NULL plane or bad depth");
+        void *d = ctx->blend.as<char>() + 4 * n * c;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d, planes[c], 4 * n, cudaMemcpyHostToDevice, st));
+        A.plane[c] = d; A.is_int[c] = is_int[c]; A.depth[c] = depth[c];
+    }
+    A.n_channels = n_channels; A.n_color = n_color; A.linear = linear; A.h = h; A.w = w; A.bits = bits;
+    A.out = (unsigned char *)(ctx->blend.as<char>() + ((4 * n * n_channels + 63) & ~(size_t)63));
+    k8_pack_samples<<<min(ctx->sms * 8, ceil_div((int)std::min<size_t>(n, 1u << 30), 256)), 256, 0, st>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, A.out, obytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
 }  // extern "C"

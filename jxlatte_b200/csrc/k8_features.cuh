@@ -200,3 +200,45 @@ __global__ void k8_splines(float *p0, float *p1, float *p2, int h, int w, const 
     }
     if (inside) { p0[(size_t)y * w + x] = acc[0]; p1[(size_t)y * w + x] = acc[1]; p2[(size_t)y * w + x] = acc[2]; }
 }
+
+// ---- PNG-ready samples: JXLImage.transfer (TF_SRGB.fromLinearF, J/color/TransferFunction.java:39-43) + ImageBuffer
+// castToIntWithMax / clamp (J/util/ImageBuffer.java:129-160) + PNGWriter's sample interleave (J/io/PNGWriter.java:191-203) ----
+struct PackArgs {
+    const void *plane[8];
+    int is_int[8], depth[8];
+    int n_channels, n_color, linear, h, w, bits;
+    unsigned char *out;
+};
+
+__device__ __forceinline__ int java_f2i(float v) {        // (int) cast of the JVM: NaN -> 0, saturating
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return -2147483647 - 1;
+    return (int)v;
+}
+
+__global__ void k8_pack_samples(PackArgs A) {
+    const long long n = (long long)A.h * A.w;
+    const int maxv = (1 << A.bits) - 1, bytes = A.bits > 8 ? 2 : 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned char *o = A.out + i * A.n_channels * bytes;
+        for (int c = 0; c < A.n_channels; c++) {
+            int q;
+            if (A.is_int[c] && A.depth[c] == A.bits) {
+                q = ((const int *)A.plane[c])[i];
+            } else {
+                float v;
+                if (A.is_int[c]) v = __fmul_rn((float)((const int *)A.plane[c])[i], __fdiv_rn(1.0f, (float)((1 << A.depth[c]) - 1)));
+                else v = ((const float *)A.plane[c])[i];
+                if (A.linear && c < A.n_color) {
+                    if (v < 0.00313066844250063f) v = __fmul_rn(v, 12.92f);
+                    else v = __fadd_rn(__fmul_rn(1.055f, (float)pow((double)v, 0.4166666666666667)), -0.055f);
+                }
+                q = java_f2i(__fadd_rn(__fmul_rn(v, (float)maxv), 0.5f));
+            }
+            q = q < 0 ? 0 : (q > maxv ? maxv : q);
+            if (bytes == 2) { o[2 * c] = (unsigned char)(q >> 8); o[2 * c + 1] = (unsigned char)(q & 255); }
+            else o[c] = (unsigned char)q;
+        }
+    }
+}

@@ -66,6 +66,9 @@ class CudaEngine:
     def upsample(self, plane, k, weights):
         return self.rec.performUpsampling(plane, k, weights)
 
+    def pack(self, channels, depths, n_color, linear, bits):
+        return self.rec.packSamples(channels, depths, n_color, linear, bits)
+
     def noise(self, planes, group_dim, seed0, lut, base_x, base_b):
         return self.rec.synthesizeNoise(planes, group_dim, seed0, lut, base_x, base_b)
 
@@ -179,19 +182,27 @@ class JXLImage:
         q = np.where(np.isnan(q), 0, q)
         return np.clip(q.astype(np.int64), 0, maxv).astype(np.uint16 if bits > 8 else np.uint8)
 
-    def write_png(self, path, bits=8):
-        q = self.to_int(bits)
-        c = q.shape[0]
-        ctype = {1: 0, 2: 4, 3: 2, 4: 6}[c]
-        rows = np.moveaxis(q, 0, 2)
+    def packed(self, bits=8, engine=None):
+        """uint8 [h, w, C * bits/8] in PNG sample order (big-endian for 16 bit).  With an engine the transfer function,
+        quantisation and interleave run on the GPU (jxlb200_pack_samples); without one, in numpy (the PNGWriter mirror)."""
+        if engine is not None:
+            depths = [self._depth(i) for i in range(len(self.channels))]
+            return engine.pack(self.channels, depths, self.info["color_channels"], self.linear, bits)
+        rows = np.moveaxis(self.to_int(bits), 0, 2)
         if bits > 8:
             rows = rows.astype(">u2")
+        return np.ascontiguousarray(rows).view(np.uint8).reshape(rows.shape[0], rows.shape[1], -1)
+
+    def write_png(self, path, bits=8, engine=None):
+        rows = self.packed(bits, engine)
+        c = len(self.channels)
+        ctype = {1: 0, 2: 4, 3: 2, 4: 6}[c]
         raw = b"".join(b"\x00" + rows[y].tobytes() for y in range(rows.shape[0]))
 
         def chunk(tag, data):
             return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
         with open(path, "wb") as f:
-            f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", q.shape[2], q.shape[1], 16 if bits > 8 else 8, ctype, 0, 0, 0)) +
+            f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", self.width, self.height, 16 if bits > 8 else 8, ctype, 0, 0, 0)) +
                     chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
     def write_pfm(self, path):

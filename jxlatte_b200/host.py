@@ -252,6 +252,19 @@ class Reconstructor:
                                             _ptr(cf), int(quant_adjust), float(base_corr_x), float(base_corr_b)))
         return np.stack(buf)
 
+    # -- PNG samples (JXLImage.transfer + ImageBuffer.castToInt + PNGWriter interleave) --
+    def packSamples(self, channels, depths, n_color, linear, bits):
+        """channels: 2-D float32 / int32 arrays of one size -> uint8 [h, w, C * bits/8], big-endian for 16 bit."""
+        ch = [np.ascontiguousarray(c if c.dtype == np.float32 else c.astype(np.int32)) for c in channels]
+        h, w = ch[0].shape
+        n = len(ch)
+        ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in ch])
+        is_int = np.array([c.dtype != np.float32 for c in ch], np.int32)
+        dep = np.array(depths, np.int32)
+        out = np.empty((h, w, n * (2 if bits > 8 else 1)), np.uint8)
+        self._check(self._L.jxlb200_pack_samples(self._h, ptrs, _ptr(is_int), _ptr(dep), n, int(n_color), int(bool(linear)), h, w, int(bits), _ptr(out)))
+        return out
+
     # -- blending (JXLCodestreamDecoder.blendAdd / blendMult / blendBlend / blendMulAdd) --
     def blend(self, op, canvas, a, b, fa=None, ra=None):
         """One rectangle of one channel; op = dict(mode, is_int, is_alpha, has_extra, clamp, premult); canvas, a (the Java's

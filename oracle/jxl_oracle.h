@@ -100,6 +100,8 @@ void orc_noise(float *const planes[3], int32_t h, int32_t w, int32_t group_dim, 
     float base_x, float base_b);
 int32_t orc_splines(float *const planes[3], int32_t h, int32_t w, int32_t num_splines, const int32_t *npoints, const int32_t *points,
     const int32_t *coeff, int32_t quant_adjust, float base_x, float base_b);
+void orc_pack_samples(const void *const *planes, const int32_t *is_int, const int32_t *depth, int32_t n_channels, int32_t n_color,
+    int32_t linear, int32_t h, int32_t w, int32_t bits, uint8_t *out);
 int32_t orc_vardct_reconstruct(const orc_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,

@@ -373,3 +373,19 @@ def splines(planes, splines_list, quant_adjust, base_x, base_b):
     if rc:
         raise RuntimeError("orc_splines rc=%d" % rc)
     return np.stack(buf)
+
+
+def pack_samples(channels, depths, n_color, linear, bits):
+    """PNGWriter's sample pipeline -> uint8 [h, w, C * bits/8] (big-endian for 16 bit)."""
+    L = lib()
+    ch = [np.ascontiguousarray(c) for c in channels]
+    h, w = ch[0].shape
+    n = len(ch)
+    ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in ch])
+    is_int = np.array([c.dtype != np.float32 for c in ch], np.int32)
+    dep = np.array(depths, np.int32)
+    out = np.zeros((h, w, n * (2 if bits > 8 else 1)), np.uint8)
+    L.orc_pack_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.orc_pack_samples.restype = None
+    L.orc_pack_samples(ptrs, is_int.ctypes.data, dep.ctypes.data, n, int(n_color), int(bool(linear)), h, w, int(bits), out.ctypes.data)
+    return out

@@ -1612,3 +1612,32 @@ int32_t orc_splines(float *const planes[3], int32_t h, int32_t w, int32_t num_sp
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * PNG samples: TF_SRGB.fromLinearF (J/color/TransferFunction.java:39-43), ImageBuffer.castToInt0 / clamp
+ * (J/util/ImageBuffer.java:129-160), PNGWriter sample order (J/io/PNGWriter.java:191-203).  out: big-endian when bits == 16.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_pack_samples(const void *const *planes, const int32_t *is_int, const int32_t *depth, int32_t n_channels, int32_t n_color,
+    int32_t linear, int32_t h, int32_t w, int32_t bits, uint8_t *out) {
+    const int maxValue = ~(~0 << bits), bytes = bits > 8 ? 2 : 1;
+    const size_t n = (size_t)h * w;
+    for (size_t i = 0; i < n; i++)
+        for (int c = 0; c < n_channels; c++) {
+            int v;
+            if (is_int[c] && depth[c] == bits) {
+                v = ((const int32_t *)planes[c])[i];
+            } else {
+                float f;
+                if (is_int[c]) { float scaleFactor = 1.0f / (float)(~(~0 << depth[c])); f = ((const int32_t *)planes[c])[i] * scaleFactor; }
+                else f = ((const float *)planes[c])[i];
+                if (linear && c < n_color) {
+                    if (f < 0.00313066844250063f) f = f * 12.92f;
+                    else f = 1.055f * (float)pow(f, 0.4166666666666667) + -0.055f;
+                }
+                v = java_f2i(f * (float)maxValue + 0.5f);
+            }
+            v = v < 0 ? 0 : v > maxValue ? maxValue : v;
+            uint8_t *o = out + (i * n_channels + c) * bytes;
+            if (bytes == 2) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)(v & 255); } else o[0] = (uint8_t)v;
+        }
+}

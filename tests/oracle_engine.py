@@ -56,6 +56,9 @@ class OracleEngine:
     def upsample(self, plane, k, weights):
         return orc.upsample(plane, k, weights)
 
+    def pack(self, channels, depths, n_color, linear, bits):
+        return orc.pack_samples(channels, depths, n_color, linear, bits)
+
     def noise(self, planes, group_dim, seed0, lut, base_x, base_b):
         return orc.noise(planes, group_dim, seed0, lut, base_x, base_b)
 

@@ -241,3 +241,33 @@ def test_spline_rendering_matches_oracle(recon):
     assert float(np.abs(want - pl).max()) > 0.05                       # something was drawn
     assert float(np.abs(got - want).max()) <= 1e-6
     assert float((got != want).mean()) < 1e-4
+
+
+def test_png_sample_packing_oracle_vs_numpy_mirror():
+    """orc_pack_samples (C restatement of TF_SRGB.fromLinearF + castToInt + interleave) == JXLImage.to_int (numpy mirror)."""
+    from oracle_engine import OracleEngine
+    eng = OracleEngine()
+    for name in ("lenna", "patches-lossless", "blendmodes_5"):
+        img = JXLDecoder(os.path.join(S, name + ".jxl"), engine=eng).decode()
+        for bits in (8, 16):
+            assert np.array_equal(img.packed(bits, engine=eng), img.packed(bits))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lenna", "patches-lossless", "blendmodes_5", "bench"])
+def test_gpu_png_sample_packing(name):
+    """jxlb200_pack_samples vs the oracle: the device's double pow and the host libm may round the last bit of a double
+    differently, so a sample may differ by one step once in ~1e8; anything more is a bug."""
+    from oracle_engine import OracleEngine
+    from jxlatte_b200.decoder import CudaEngine
+    eng, ref = CudaEngine(), OracleEngine()
+    img = JXLDecoder(os.path.join(S, name + ".jxl"), engine=ref).decode()
+    for bits in (8, 16):
+        got, want = img.packed(bits, engine=eng), img.packed(bits, engine=ref)
+        assert got.shape == want.shape
+        if bits == 8:
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        else:
+            d = np.abs(got.view(">u2").astype(np.int32) - want.view(">u2").astype(np.int32))
+        assert int(d.max()) <= 1 and float((d != 0).mean()) < 1e-6
+    eng.close()

@@ -45,7 +45,7 @@ def main():
         if a.output.endswith(".pfm"):
             img.write_pfm(a.output)
         else:
-            img.write_png(a.output, a.bits)
+            img.write_png(a.output, a.bits, engine=engine)
     engine.close()
 
 

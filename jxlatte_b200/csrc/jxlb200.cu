@@ -23,6 +23,10 @@
 #include "qm_tables.cuh"
 
 // grow-only device allocation
+#ifndef JXLB200_OVERLAP_ROWS
+#define JXLB200_OVERLAP_ROWS 0   /* measured on B200, 8K frame: off 3.46 ms; 512 rows 4.29; 1024 3.79; 2048 3.62 -- per-slab launch tails cost more than the overlap wins */
+#endif
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -50,6 +54,8 @@ struct jxlb200_ctx {
     int64_t launches = 0;
     bool have_weights = false;
     int opt_stage2 = 0;
+    int opt_overlap_rows = JXLB200_OVERLAP_ROWS;   // device-resident whole path: slab height for overlapping stage 2 of slab j with stage 1 of slab j+2 (0 = off)
+    std::vector<cudaEvent_t> ev_pool;
 
     DevBuf sched, items, gate, wraw, woff, wexp, cosbig, lut8, sigma, flags;
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
@@ -520,6 +526,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
                      &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend};
     for (DevBuf *b : all) b->release();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     for (int i = 0; i < 6; i++) { if (ctx->k1_stream[i]) cudaStreamDestroy(ctx->k1_stream[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
@@ -548,6 +555,7 @@ int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0;
 int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return JXLB200_E_ARG;
     if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 2) { ctx->opt_stage2 = value; return 0; }
+    if (option == JXLB200_OPT_OVERLAP_ROWS && value >= 0 && (value & 255) == 0) { ctx->opt_overlap_rows = value; return 0; }
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
 
@@ -614,6 +622,52 @@ int32_t jxlb200_vardct_reconstruct_dev(jxlb200_ctx *ctx, const jxlb200_frame_par
     const size_t plane = (size_t)p->width * p->height;
     CUDA_TRY(ctx, ctx->mid.ensure(sizeof(float) * 3 * plane));
     float *mid[3] = {ctx->mid.as<float>(), ctx->mid.as<float>() + plane, ctx->mid.as<float>() + 2 * plane};
+    const int W = p->width, H = p->height, wb = W >> 3, tw = (W + 63) >> 6;
+    const int SL = ctx->opt_overlap_rows;
+    if (!is_subsampled(p) && SL >= 256 && H >= 2 * SL) {
+        // Stage 1 is short of warps per SM, stage 2 short of issue slots it can fill on its own: run them side by side.
+        // The frame is cut into slabs of group rows; stage 1 walks the slabs on the main stream, stage 2 of slab j follows on a
+        // second stream as soon as stage 1 of slab j+1 (its lower halo rows) is done, so it overlaps stage 1 of slab j+2.
+        const int nslab = ceil_div(H, SL);
+        while ((int)ctx->ev_pool.size() < nslab + 1) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_pool.push_back(e);
+        }
+        cudaStream_t main = ctx->stream, side = ctx->d2h_stream;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[nslab], main));       // the side stream starts after whatever precedes this call
+        CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_pool[nslab], 0));
+        for (int i = 0; i <= nslab; i++) {
+            if (i < nslab) {
+                const int y0 = i * SL, rows = std::min(SL, H - y0);
+                jxlb200_frame_params ps = *p;
+                ps.height = rows;
+                const int32_t *q3[3] = {qcoeff[0] + (size_t)y0 * W, qcoeff[1] + (size_t)y0 * W, qcoeff[2] + (size_t)y0 * W};
+                const float *l3[3] = {lf[0] + (size_t)(y0 / 8) * wb, lf[1] + (size_t)(y0 / 8) * wb, lf[2] + (size_t)(y0 / 8) * wb};
+                float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
+                rc = invert_dev(ctx, &ps, q3, l3, dct_select + (size_t)(y0 / 8) * wb, block_origin + (size_t)(y0 / 8) * wb, hf_mul + (size_t)(y0 / 8) * wb,
+                                x_from_y + (size_t)(y0 / 64) * tw, b_from_y + (size_t)(y0 / 64) * tw, m3, W);
+                if (rc) return rc;
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[i], main));
+            }
+            if (i >= 1) {
+                const int j = i - 1, y0 = j * SL, rows = std::min(SL, H - y0);
+                CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_pool[std::min(i, nslab - 1)], 0));
+                jxlb200_frame_params ps = *p;
+                ps.height = rows;
+                jxlb200_slab sl = {y0, rows, H, j > 0 ? 1 : 0, j < nslab - 1 ? 1 : 0};
+                const float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
+                float *o3[3] = {out[0] + (size_t)y0 * W, out[1] + (size_t)y0 * W, out[2] + (size_t)y0 * W};
+                ctx->stream = side;
+                rc = restore_dev(ctx, &ps, &sl, m3, W, hf_mul + (size_t)(y0 / 8) * wb, sharpness ? sharpness + (size_t)(y0 / 8) * wb : nullptr, o3);
+                ctx->stream = main;
+                if (rc) return rc;
+            }
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[nslab], side));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_pool[nslab], 0));
+        return 0;
+    }
     rc = is_subsampled(p) ? invert_subsampled_dev(ctx, p, qcoeff, lf, dct_select, hf_mul, mid)
                           : invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, p->width);
     if (rc) return rc;

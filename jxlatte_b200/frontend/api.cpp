@@ -80,6 +80,18 @@ void describe(jxlf_image &im) {
         j.close('}');
     }
     j.close(']');
+    {
+        Coverage &c = coverage();
+        j.open("coverage", '{');
+        j.num("entropy_streams", c.streams.load()); j.num("ans", c.ans_streams.load()); j.num("prefix", c.prefix_streams.load());
+        j.num("lz77_streams", c.lz77_streams.load()); j.num("lz77_copies", c.lz77_copies.load()); j.num("mtf_context_maps", c.mtf_context_maps.load());
+        j.num("permuted_toc", c.permuted_toc.load()); j.num("coded_coefficient_orders", c.coded_orders.load());
+        j.num("multi_pass_frames", c.multi_pass_frames.load()); j.num("custom_block_contexts", c.custom_block_ctx.load());
+        j.num("weighted_predictor_channels", c.wp_channels.load()); j.num("global_trees", c.global_trees.load()); j.num("local_trees", c.local_trees.load());
+        j.num("squeeze", c.squeeze.load()); j.num("palette", c.palette.load()); j.num("delta_palette", c.delta_palette.load()); j.num("rct", c.rct.load());
+        j.num("raw_quant_tables", c.raw_quant.load()); j.num("custom_quant_tables", c.custom_quant.load()); j.num("lf_smoothing_groups", c.lf_smoothing.load());
+        j.close('}');
+    }
     j.open("frames", '[');
     for (auto &fp : im.frames) {
         const FrameData &f = *fp;
@@ -190,6 +202,7 @@ extern "C" {
 int32_t jxlf_decode(const uint8_t *data, uint64_t size, int32_t flags, jxlf_image **out) {
     if (!data || !out) return -1;
     auto im = std::make_unique<jxlf_image>();
+    coverage().reset();
     try {
         std::vector<uint8_t> file(data, data + size);
         const int level = extract_codestream(file, im->codestream);

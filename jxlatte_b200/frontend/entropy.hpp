@@ -4,11 +4,26 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <memory>
 
 #include "bits.hpp"
 
 namespace jxlf {
+
+// which optional coding tools a stream actually used (reported in jxlf_describe: tells what the samples do and do not exercise)
+struct Coverage {
+    typedef std::atomic<long> N;      // group sections are decoded on several threads
+    N streams{0}, lz77_streams{0}, prefix_streams{0}, ans_streams{0}, mtf_context_maps{0}, lz77_copies{0};
+    N permuted_toc{0}, coded_orders{0}, multi_pass_frames{0}, custom_block_ctx{0}, wp_channels{0}, global_trees{0}, local_trees{0};
+    N squeeze{0}, palette{0}, delta_palette{0}, rct{0}, raw_quant{0}, custom_quant{0}, lf_smoothing{0};
+    void reset() {
+        for (N *p : {&streams, &lz77_streams, &prefix_streams, &ans_streams, &mtf_context_maps, &lz77_copies, &permuted_toc, &coded_orders,
+                     &multi_pass_frames, &custom_block_ctx, &wp_channels, &global_trees, &local_trees, &squeeze, &palette, &delta_palette,
+                     &rct, &raw_quant, &custom_quant, &lf_smoothing}) *p = 0;
+    }
+};
+inline Coverage &coverage() { static Coverage c; return c; }
 
 struct HybridConfig {
     int split_exp = 0, msb = 0, lsb = 0;
@@ -109,6 +124,7 @@ class EntropyStream {
             distance = std::min<int64_t>(distance, 1 << 20);
             distance = std::min<int64_t>(distance, decoded_);
             copy_pos_ = decoded_ - (uint32_t)distance;
+            coverage().lz77_copies++;
             if (to_copy_ == 0) throw StreamError("LZ77 copy of zero length");
             return copy_one();
         }
@@ -132,6 +148,7 @@ class EntropyStream {
                 for (auto &m : map) m = (uint8_t)br.bits(nbits);
             } else {
                 const bool mtf = br.flag();
+                if (mtf) coverage().mtf_context_maps++;
                 EntropyStream nested;
                 nested.read_header(br, 1, num_dists <= 2);
                 std::vector<uint32_t> raw(num_dists);
@@ -216,7 +233,9 @@ class EntropyStream {
         if (num_dists <= 0) throw std::logic_error("entropy stream needs at least one context");
         auto s = std::make_shared<Shared>();
         s->lz77 = br.flag();
+        coverage().streams++;
         if (s->lz77) {
+            coverage().lz77_streams++;
             if (forbid_lz77) throw StreamError("nested entropy stream may not use LZ77");
             s->lz_min_symbol = br.u32(224, 0, 512, 0, 4096, 0, 8, 15);
             s->lz_min_length = br.u32(3, 0, 4, 0, 5, 2, 9, 8);
@@ -227,6 +246,7 @@ class EntropyStream {
         const int clusters = read_cluster_map(br, s->cluster, num_dists, num_dists);
         s->dists.resize(clusters);
         s->prefix = br.flag();
+        (s->prefix ? coverage().prefix_streams : coverage().ans_streams)++;
         s->log_alphabet = s->prefix ? 15 : 5 + (int)br.bits(2);
         for (auto &d : s->dists) d.cfg.read(br, s->log_alphabet);
         if (s->prefix) {

@@ -87,6 +87,7 @@ class FrameDecoder {
             f.padded_h = ceil_div(h.height, fy) * fy;
             f.padded_w = ceil_div(h.width, fx) * fx;
         }
+        if (f.hdr.num_passes > 1) coverage().multi_pass_frames++;
         read_toc(f);
     }
     size_t frame_bytes() const { size_t n = 0; for (auto l : toc_len_) n += l; return n; }
@@ -164,6 +165,7 @@ class FrameDecoder {
         const size_t entries = (f.num_groups == 1 && f.hdr.num_passes == 1) ? 1 : 2 + f.num_lf_groups + (size_t)f.num_groups * f.hdr.num_passes;
         toc_perm_.clear();
         if (br_.flag()) {
+            coverage().permuted_toc++;
             EntropyStream es(br_, 8);
             toc_perm_ = read_permutation(br_, es, (uint32_t)entries, 0);
             es.expect_final_state("TOC permutation");
@@ -319,6 +321,7 @@ class FrameDecoder {
             num_lf_contexts_ = 1;
             return;
         }
+        coverage().custom_block_ctx++;
         int lf_ctx = 1, size = 39;
         for (auto &t : lf_thresholds_) {
             t.resize(br.bits(4));
@@ -474,7 +477,7 @@ class FrameDecoder {
                 dq[2][k] += kb * dq[1][k];
             }
         }
-        if (smooth) adaptive_smooth(dq, st.bh, st.bw);
+        if (smooth) { adaptive_smooth(dq, st.bh, st.bw); coverage().lf_smoothing++; }
         // stitch into the frame-level LF planes
         const int gy = g / f.lf_group_cols, gx = g % f.lf_group_cols;
         for (int i = 0; i < 3; i++) {
@@ -616,6 +619,7 @@ class FrameDecoder {
                 QuantParams &q = f.qparams[i];
                 q = QuantParams();
                 q.mode = (int)br.bits(3);
+                if (q.mode == 7) coverage().raw_quant++; else if (q.mode != 0) coverage().custom_quant++;
                 const bool small = (i >= 0 && i <= 3) || i == 9 || i == 10;
                 if (!(q.mode == 0 || q.mode == 6 || q.mode == 7) && !small) throw StreamError("quant table encoding does not fit its transform");
                 switch (q.mode) {
@@ -720,6 +724,7 @@ class FrameDecoder {
             }
             if (h.encoding != ENC_VARDCT) continue;
             const uint32_t used = br.u32(0x5f, 0, 0x13, 0, 0, 0, 0, 13);
+            if (used) coverage().coded_orders++;
             EntropyStream es;
             if (used) es = EntropyStream(br, 8);
             for (int b = 0; b < 13; b++) {

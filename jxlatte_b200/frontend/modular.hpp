@@ -219,6 +219,12 @@ class ModularStream {
         transforms.resize(nb_transforms);
         for (auto &t : transforms) read_transform(br, t);
         for (auto &t : transforms) replay_transform(t);
+        for (auto &t : transforms) {
+            if (t.tr == TR_SQUEEZE) coverage().squeeze++;
+            else if (t.tr == TR_RCT) coverage().rct++;
+            else { coverage().palette++; if (t.nb_deltas > 0) coverage().delta_palette++; }
+        }
+        (use_global_tree ? coverage().global_trees : coverage().local_trees)++;
         if (!use_global_tree) {
             local_tree_.read(br);
             tree_ = &local_tree_;
@@ -375,6 +381,7 @@ class ModularStream {
         ch.decoded = true;
         ch.allocate();
         const bool use_wp = ch.force_wp || tree_->uses_wp;
+        if (use_wp) coverage().wp_channels++;
         const int H = ch.h, W = ch.w;
         std::vector<int32_t> err[5];
         std::vector<int32_t> wp_pred;

@@ -113,6 +113,8 @@ void describe(jxlf_image &im) {
         j.farr("epf_channel_scale", h.rf.channel_scale, h.rf.channel_scale + 3);
         j.flt("epf_pass0_sigma_scale", h.rf.pass0_sigma_scale); j.flt("epf_pass2_sigma_scale", h.rf.pass2_sigma_scale);
         j.flt("epf_border_sad_mul", h.rf.border_sad_mul); j.flt("epf_sigma_for_modular", h.rf.sigma_for_modular);
+        j.num("toc_bit_offset", (unsigned long long)f.toc_bit_offset); j.num("toc_first_section", (unsigned long long)f.toc_first_section);
+        j.iarr("toc_lengths", f.toc_lengths.begin(), f.toc_lengths.end());
         j.num("num_groups", f.num_groups); j.num("num_lf_groups", f.num_lf_groups);
         j.farr("lf_dequant", f.lf_dequant, f.lf_dequant + 3); j.num("global_scale", f.global_scale); j.num("quant_lf", f.quant_lf);
         j.num("color_factor", f.color_factor); j.flt("base_corr_x", f.base_corr_x); j.flt("base_corr_b", f.base_corr_b);

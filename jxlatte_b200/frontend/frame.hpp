@@ -41,6 +41,8 @@ struct FrameData {
     FrameHeader hdr;
     int padded_w = 0, padded_h = 0;            // Frame.getPaddedFrameSize
     int num_groups = 0, num_lf_groups = 0, group_cols = 0, lf_group_cols = 0;
+    uint64_t toc_bit_offset = 0, toc_first_section = 0;      // where the TOC starts (bits) and where the first section starts (bytes), in the codestream
+    std::vector<uint32_t> toc_lengths;
     // LFGlobal
     float lf_dequant[3] = {1.0f / 4096, 1.0f / 512, 1.0f / 256};
     int global_scale = 0, quant_lf = 0;
@@ -162,6 +164,7 @@ class FrameDecoder {
         return perm;
     }
     void read_toc(FrameData &f) {
+        f.toc_bit_offset = br_.position();
         const size_t entries = (f.num_groups == 1 && f.hdr.num_passes == 1) ? 1 : 2 + f.num_lf_groups + (size_t)f.num_groups * f.hdr.num_passes;
         toc_perm_.clear();
         if (br_.flag()) {
@@ -175,6 +178,8 @@ class FrameDecoder {
         for (auto &l : toc_len_) l = br_.u32(0, 10, 1024, 14, 17408, 22, 4211712, 30);
         br_.align();
         toc_start_ = (size_t)(br_.position() >> 3);
+        f.toc_first_section = toc_start_;
+        f.toc_lengths.assign(toc_len_.begin(), toc_len_.end());
     }
     void open_sections() {
         sections_.clear();

@@ -271,3 +271,71 @@ def test_gpu_png_sample_packing(name):
             d = np.abs(got.view(">u2").astype(np.int32) - want.view(">u2").astype(np.int32))
         assert int(d.max()) <= 1 and float((d != 0).mean()) < 1e-6
     eng.close()
+
+
+class _BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def put(self, value, n):
+        for i in range(n):
+            self.bits.append((value >> i) & 1)
+
+    def align(self):
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def tobytes(self):
+        self.align()
+        out = bytearray(len(self.bits) // 8)
+        for i, b in enumerate(self.bits):
+            out[i >> 3] |= b << (i & 7)
+        return bytes(out)
+
+
+def _u32_toc_len(w, v):
+    """U32(u(10), 1024 + u(14), 17408 + u(22), 4211712 + u(30)) as Frame.readTOC reads it."""
+    for sel, (base, nbits) in enumerate(((0, 10), (1024, 14), (17408, 22), (4211712, 30))):
+        if v - base < (1 << nbits) and v >= base:
+            w.put(sel, 2)
+            w.put(v - base, nbits)
+            return
+    raise ValueError(v)
+
+
+def test_permuted_toc_crafted_from_lenna():
+    """No sample uses a permuted TOC, so one is crafted: lenna's sections are stored with the first two swapped and a TOC
+    permutation (a Lehmer code behind a one-symbol prefix code) that swaps them back.  The parsed state must be identical."""
+    data = open(os.path.join(S, "lenna.jxl"), "rb").read()
+    base = frontend.parse(data)
+    f = base.frames[0]
+    assert data[:2] == b"\xff\x0a" and not base.info["coverage"]["permuted_toc"]
+    lengths, first, tbit = f["toc_lengths"], f["toc_first_section"], f["toc_bit_offset"]
+    assert len(lengths) == 7
+    secs, at = [], first
+    for n in lengths:
+        secs.append(data[at:at + n])
+        at += n
+    w = _BitWriter()
+    for i in range(tbit):                       # everything before the TOC, bit for bit
+        w.bits.append((data[i >> 3] >> (i & 7)) & 1)
+    w.put(1, 1)                                 # permuted
+    # EntropyStream(8 contexts): no LZ77; simple cluster map with 0 bits per entry; prefix codes; hybrid config 15-0-0
+    w.put(0, 1)
+    w.put(1, 1); w.put(0, 2)
+    w.put(1, 1)
+    w.put(15, 4)
+    w.put(1, 1); w.put(0, 4); w.put(0, 0)       # alphabet size 1 + (1 << 0) + u(0) = 2
+    w.put(1, 2); w.put(0, 2); w.put(1, 1)       # simple prefix code, one symbol, value 1 (1 bit wide)
+    # end = 1, lehmer[0] = 1: both are the symbol "1", which costs no bits -> permutation [1, 0, 2, 3, 4, 5, 6]
+    w.align()
+    phys = [secs[1], secs[0]] + secs[2:]        # logical section i lives at physical position perm[i]
+    for s_ in phys:
+        _u32_toc_len(w, len(s_))
+    w.align()
+    crafted = w.tobytes() + b"".join(phys) + data[at:]
+    got = frontend.parse(crafted)
+    assert got.info["coverage"]["permuted_toc"] == 1
+    a, b = base.vardct_state(0), got.vardct_state(0)
+    for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y"):
+        assert np.array_equal(a[k], b[k]), k

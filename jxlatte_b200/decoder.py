@@ -312,13 +312,24 @@ class JXLDecoder:
             bufs = [_Buf(np.ascontiguousarray(rec[c][:h, :w])) for c in range(3)]
             first = 0
         else:
-            if info["xyb_encoded"]:
-                raise NotImplementedError("XYB-encoded Modular frames")
             if f["do_ycbcr"]:
                 raise NotImplementedError("YCbCr Modular frames")
-            ncol = info["color_channels"]
-            bufs = [_Buf(np.ascontiguousarray(mod[c][:h, :w])) for c in range(ncol)]          # int32 samples (Frame.java:452-455)
-            first = ncol
+            if f["gab"] or f["epf_iters"] > 0:
+                raise NotImplementedError("Gaborish / EPF on Modular frames (constant-sigma EPF, frame sizes that are not multiples of 8)")
+            if info["xyb_encoded"]:
+                # lossy Modular: channels are Y, X, B - Y in integers; Frame.decodeFrame :429-447 scales them by LFGlobal.lfDequant
+                # (X, Y, B order) into float XYB planes, which then take the same colour transform as VarDCT frames
+                dq = [np.float32(v) for v in f["lf_dequant"]]
+                y, x, b = (np.ascontiguousarray(mod[c][:h, :w]) for c in range(3))
+                planes = [dq[0] * x.astype(np.float32), dq[1] * y.astype(np.float32), dq[2] * (y + b).astype(np.float32)]
+                bufs = [_Buf(np.ascontiguousarray(pl, np.float32)) for pl in planes]
+                p = self.frame_params(info, dict(f, padded_width=-(-w // 8) * 8, padded_height=-(-h // 8) * 8, global_scale=1))
+                pending = True
+                first = 3
+            else:
+                ncol = info["color_channels"]
+                bufs = [_Buf(np.ascontiguousarray(mod[c][:h, :w])) for c in range(ncol)]          # int32 samples (Frame.java:452-455)
+                first = ncol
         for e in range(len(info["extra_channels"])):
             bufs.append(_Buf(np.ascontiguousarray(mod[first + e][:h, :w])))
         return bufs, pending, p
@@ -470,11 +481,16 @@ class JXLDecoder:
                 for c in range(3):
                     bufs[c].a = np.ascontiguousarray(xyb[c])
             if pending:
+                hh, ww = bufs[0].a.shape
+                ph, pw = -(-hh // 8) * 8, -(-ww // 8) * 8          # the ABI takes padded planes; the transform is per pixel
                 q = p.copy()
-                q.width, q.height = bufs[0].a.shape[1], bufs[0].a.shape[0]
-                rgb = self.engine.color(q, np.stack([bufs[c].a for c in range(3)]))
+                q.width, q.height = pw, ph
+                xyb = np.zeros((3, ph, pw), np.float32)
                 for c in range(3):
-                    bufs[c] = _Buf(np.ascontiguousarray(rgb[c]))
+                    xyb[c, :hh, :ww] = bufs[c].a
+                rgb = self.engine.color(q, xyb)
+                for c in range(3):
+                    bufs[c] = _Buf(np.ascontiguousarray(rgb[c, :hh, :ww]))
             if canvas is None:
                 dt = bufs[0].a.dtype
                 canvas = [_Buf(np.zeros((info["height"], info["width"]), dt)) for _ in range(colors + nextra)]

@@ -282,11 +282,9 @@ class JXLDecoder:
         return out
 
     # ---- one frame: Frame.decodeFrame (+ the colour transform when nothing has to happen in between) ----
-    def decode_frame(self, parsed, k):
+    def decode_frame(self, parsed, k, lf_store=None):
         """-> (list of _Buf of frame size: colour channels then extra channels, colour transform still pending?, params)."""
         info, f = parsed.info, parsed.frames[k]
-        if f["flags"] & FLAG_USE_LF_FRAME:
-            raise NotImplementedError("frames that take their LF from an LF frame: SURVEY.md 8f-3")
         h, w = f["height"], f["width"]
         bits = info["bits_per_sample"]
         mod = None
@@ -300,6 +298,22 @@ class JXLDecoder:
             st = parsed.vardct_state(k)
             st["qm_weights"], st["qm_offsets"] = self.quant_tables(parsed, k, f)
             p = self.frame_params(info, f)
+            if f["flags"] & FLAG_USE_LF_FRAME:
+                # LFCoefficients.java:39-52: dequantLFCoeff is cut out of the LF frame stored for this level
+                src = lf_store[f["lf_level"]] if lf_store else None
+                if src is None:
+                    raise frontend.InvalidBitstreamError("LF Level too large")
+                bh, bw = f["padded_height"] // 8, f["padded_width"] // 8
+                lf = np.zeros((3, bh, bw), np.float32)
+                for c in range(3):
+                    src[c].cast_to_float(info["bits_per_sample"])
+                    a = src[c].a[:bh, :bw]
+                    if a.shape != (bh, bw):
+                        raise frontend.InvalidBitstreamError("LF frame smaller than the frame that uses it")
+                    lf[c] = a
+                st["lf"] = lf
+            if f["type"] == 1:
+                p.color_mode = 0                      # LF frames are kept as they leave Frame.decodeFrame (no colour transform)
             # patches and saveBeforeCT act on the planes BEFORE the colour transform (JXLCodestreamDecoder.java:611-616)
             upsampled = f["upsampling"] != 1 or any(u != 1 for u in f["ec_upsampling"])
             pending = p.color_mode != 0 and (bool(f["flags"] & (FLAG_PATCHES | FLAG_SPLINES | FLAG_NOISE)) or f["save_before_ct"] or upsampled)
@@ -443,10 +457,13 @@ class JXLDecoder:
         linear = bool(info["xyb_encoded"])
         t1 = time.perf_counter()
         visible_frames = invisible_frames = 0
+        lf_store = [None] * 5                       # JXLCodestreamDecoder.lfBuffer
         for k, f in enumerate(parsed.frames):
-            if f["type"] == 1 or f["lf_level"] > 0:
-                raise NotImplementedError("LF frames: SURVEY.md 8f-3")
-            bufs, pending, p = self.decode_frame(parsed, k)
+            bufs, pending, p = self.decode_frame(parsed, k, lf_store)
+            if f["lf_level"] > 0:
+                lf_store[f["lf_level"] - 1] = bufs
+            if f["type"] == 1:
+                continue
             frame_colors = 3 if (info["xyb_encoded"] or f["encoding"] == ENC_VARDCT) else colors
             save = (f["save_as_reference"] != 0 or f["duration"] == 0) and not f["is_last"] and f["type"] != 1
             if f["type"] in (0, 3) and (f["duration"] != 0 or f["is_last"]):          # Frame.isVisible

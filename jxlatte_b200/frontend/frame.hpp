@@ -449,7 +449,12 @@ class FrameDecoder {
     // LFCoefficients.java:20-98 (dequant, LF chroma-from-luma, adaptive smoothing) and :100-194
     void read_lf_coefficients(FrameData &f, BitReader &br, int g, LFGroupState &st) {
         const FrameHeader &h = f.hdr;
-        if (h.flags & FLAG_USE_LF_FRAME) throw Unsupported("frames that take their LF from an LF frame");
+        if (h.flags & FLAG_USE_LF_FRAME) {
+            // LFCoefficients.java:39-52: the LF planes are copied from the LF frame decoded earlier (the caller owns its pixels,
+            // so f.lf stays zero here and is filled in by the caller); lfIndex stays all zero
+            st.lf_index.assign((size_t)st.bh * st.bw, 0);
+            return;
+        }
         const bool subsampled = h.shift_y[0] | h.shift_y[1] | h.shift_y[2] | h.shift_x[0] | h.shift_x[1] | h.shift_x[2];
         const bool smooth = !(h.flags & FLAG_SKIP_ADAPTIVE_LF_SMOOTHING);
         if (smooth && subsampled) throw StreamError("adaptive LF smoothing with chroma subsampling");

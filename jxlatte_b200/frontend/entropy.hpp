@@ -337,7 +337,7 @@ class EntropyStream {
         // alias table (Vose with stacks, in the order the format prescribes)
         d.log_bucket = 12 - log_alphabet;
         const int bucket = 1 << d.log_bucket;
-        d.freq.assign(table, 0);
+        d.freq.assign(std::max((size_t)table, f.size()), 0);      // a one-symbol histogram may name a symbol beyond the table (the Java never checks it)
         for (size_t i = 0; i < f.size(); i++) d.freq[i] = (uint16_t)f[i];
         d.cutoff.assign(table, 0);
         d.alias.assign(table, 0);

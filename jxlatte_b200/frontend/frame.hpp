@@ -76,6 +76,10 @@ class FrameDecoder {
         br_.align();
         f.hdr.read(br_, ih_);
         const FrameHeader &h = f.hdr;
+        // crop sizes are 30-bit fields: bound what a header may make this process allocate (2^28 px = the 16384^2 config)
+        if (h.width <= 0 || h.height <= 0) throw StreamError("empty frame");
+        if ((int64_t)h.width * h.height > (1ll << 28) || h.width > (1 << 24) || h.height > (1 << 24))
+            throw Unsupported("frame larger than 2^28 pixels");
         f.group_cols = ceil_div(h.width, h.group_dim);
         f.lf_group_cols = ceil_div(h.width, h.group_dim << 3);
         f.num_groups = f.group_cols * ceil_div(h.height, h.group_dim);
@@ -157,10 +161,12 @@ class FrameDecoder {
         }
         std::vector<uint32_t> pool(size), perm(size);
         for (uint32_t i = 0; i < size; i++) pool[i] = i;
-        for (uint32_t i = 0; i < size; i++) {
+        const uint32_t coded = end + skip;          // Lehmer digits beyond this are zero: the rest of the pool follows in order
+        for (uint32_t i = 0; i < coded; i++) {
             perm[i] = pool[lehmer[i]];
             pool.erase(pool.begin() + lehmer[i]);
         }
+        std::copy(pool.begin(), pool.end(), perm.begin() + coded);
         return perm;
     }
     void read_toc(FrameData &f) {
@@ -831,6 +837,7 @@ class FrameDecoder {
                 // frame-level destination of this group's coefficient rectangle for channel c
                 const int cw = f.padded_w >> h.shift_x[c];
                 const int py0 = ((grow << 8) >> h.shift_y[c]) + (sgy << 3), px0 = ((gcol << 8) >> h.shift_x[c]) + (sgx << 3);
+                if (py0 + tt.ph > (f.padded_h >> h.shift_y[c]) || px0 + tt.pw > cw) throw StreamError("varblock leaves its (subsampled) plane");
                 int32_t *plane = f.qcoeff[c].data();
                 uint32_t prev_sym = 0;
                 for (int k = 0; k < order_size - num_blocks; k++) {

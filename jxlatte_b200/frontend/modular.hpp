@@ -201,6 +201,7 @@ class ModularStream {
 
     // frame-level stream: channel_count channels of the frame size (colour first, then extra channels with dim shifts)
     void init_global(BitReader &br, const FrameContext &fc, int index, int channel_count, int ec_start) {
+        if ((int64_t)channel_count * fc.modular_h * fc.modular_w > (1ll << 31)) throw Unsupported("more than 2^31 modular samples in one frame");
         std::vector<Channel> list;
         for (int i = 0; i < channel_count; i++) {
             const int shift = i < ec_start ? 0 : fc.ec_dim_shift[i - ec_start];

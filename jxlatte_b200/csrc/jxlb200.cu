@@ -194,7 +194,7 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     CUDA_TRY(ctx, cudaMemsetAsync(S, 0, sizeof(Sched), st));
     const int ncells = wb * hb;
     const int g0 = min(ctx->sms * 4, ceil_div(ncells, 256));
-    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, S, ctx->flags.as<int>() + 2);
+    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, wb, hb, S, ctx->flags.as<int>() + 2);
     k0_plan<<<1, 32, 0, st>>>(S);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->gate.p, 0x7f, sizeof(int) * (size_t)tw * th, st));
     k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>(), ctx->gate.as<int>(), tw);
@@ -457,7 +457,7 @@ int check_flags(jxlb200_ctx *ctx) {
     if (!e[0] && !e[2] && !e[3]) return 0;
     cudaMemset(ctx->flags.p, 0, sizeof(e));
     if (e[3]) return ctx->fail(JXLB200_E_UNSUPPORTED, "chroma subsampling with varblocks larger than 8x8");
-    if (e[2]) return ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select (HFMetadata.java:45-46)");
+    if (e[2]) return ctx->fail(JXLB200_E_STREAM, "Invalid Transform Type in dct_select, or a varblock that leaves its group (HFMetadata.java:45-46, 93-119)");
     return ctx->fail(JXLB200_E_STREAM, "Invalid EPF Sharpness (Frame.java:565-566)");
 }
 

@@ -17,7 +17,15 @@ static const int h_big_types[2][N_BIGC][3] = {
     {{19, -1, -1}, {18, 20, 22}, {21, 23, 25}, {24, 26, -1}},
 };
 
-__global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int ncells, Sched *s, int *__restrict__ err) {
+// a varblock must stay inside the frame and inside its 256x256 group (HFMetadata.placeBlock can place nothing else); the
+// kernels trust this, so a caller's inconsistent maps are rejected here instead of being written out of bounds
+__device__ __forceinline__ bool k0_valid_origin(int t, int i, int wb, int hb) {
+    const TTInfo tt = c_tt[t];
+    const int by = i / wb, bx = i - by * wb;
+    return bx + tt.bw <= wb && by + tt.bh <= hb && (by & 31) + tt.bh <= 32 && (bx & 31) + tt.bw <= 32;
+}
+
+__global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int ncells, int wb, int hb, Sched *s, int *__restrict__ err) {
     __shared__ int h[27];
     __shared__ int bad;
     if (threadIdx.x < 27) h[threadIdx.x] = 0;
@@ -25,8 +33,12 @@ __global__ void k0_count(const uint8_t *__restrict__ ds, const uint8_t *__restri
     __syncthreads();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += gridDim.x * blockDim.x) {
         const int t = ds[i];
-        if (t > 26) bad = 1;
-        else if (bo[i]) atomicAdd(&h[t], 1);
+        if (t > 26) {
+            bad = 1;
+        } else if (bo[i]) {
+            if (!k0_valid_origin(t, i, wb, hb)) bad = 1;
+            else atomicAdd(&h[t], 1);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 27 && h[threadIdx.x]) atomicAdd(&s->cnt[threadIdx.x], h[threadIdx.x]);
@@ -78,7 +90,7 @@ __global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__rest
     const int lo = blockIdx.x * per, hi = min(ncells, lo + per);
     // two sweeps over this CTA's cell range: count, reserve one range per type, then place
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x)
-        if (bo[i] && ds[i] <= 26) atomicAdd(&h[ds[i]], 1);
+        if (bo[i] && ds[i] <= 26 && k0_valid_origin(ds[i], i, wb, hb)) atomicAdd(&h[ds[i]], 1);
     __syncthreads();
     if (threadIdx.x < 27) {
         base[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&s->cursor[threadIdx.x], h[threadIdx.x]) : 0;
@@ -87,7 +99,7 @@ __global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__rest
     __syncthreads();
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const int t = ds[i];
-        if (bo[i] && t <= 26) {
+        if (bo[i] && t <= 26 && k0_valid_origin(t, i, wb, hb)) {
             const int slot = s->start[t] + base[t] + atomicAdd(&h[t], 1);
             const int by = i / wb, bx = i % wb;
             items[slot] = (by << 16) | bx;

@@ -232,3 +232,18 @@ def test_chroma_subsampling_rejects_large_varblocks(recon):
     recon.setWeights(qw, qo)
     with pytest.raises(NotImplementedError):
         recon.reconstruct(p, st)
+
+
+@pytest.mark.gpu
+def test_inconsistent_block_maps_are_rejected(recon):
+    """A block_origin / dct_select pair that HFMetadata.placeBlock could never produce (a 64x64 varblock hanging over the
+    frame edge, one crossing a group boundary) must come back as an invalid-stream error, not as out-of-bounds writes."""
+    p = default_frame_params(320, 64)
+    st = _state(320, 64, 1, p, mix="dct8")
+    for (by, bx) in ((4, 0), (0, 36), (0, 28)):          # leaves the frame at the bottom / at the right / crosses x = 256
+        bad = dict(st)
+        bad["dct_select"] = st["dct_select"].copy()
+        bad["dct_select"][by, bx] = 18                   # DCT64
+        with pytest.raises(InvalidBitstreamError):
+            recon.invertVarDCT(p, bad)
+    assert np.isfinite(recon.invertVarDCT(p, st)).all()

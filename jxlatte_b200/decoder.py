@@ -295,7 +295,7 @@ class JXLDecoder:
             mod = self.engine.modular(parsed.modular_channels(k), tr, bits)
         pending, p = False, None
         if f["encoding"] == ENC_VARDCT:
-            st = parsed.vardct_state(k)
+            st = parsed.vardct_state(k, copy=False)
             st["qm_weights"], st["qm_offsets"] = self.quant_tables(parsed, k, f)
             p = self.frame_params(info, f)
             if f["flags"] & FLAG_USE_LF_FRAME:

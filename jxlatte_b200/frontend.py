@@ -92,8 +92,9 @@ class ParsedImage:
     def frames(self):
         return self.info["frames"]
 
-    def array(self, frame, name, index=0, shape=None):
-        """numpy COPY of one named array of a frame (see jxlf_array in include/jxlfront.h)."""
+    def array(self, frame, name, index=0, shape=None, copy=True):
+        """One named array of a frame (see jxlf_array in include/jxlfront.h): a numpy copy, or with copy=False a read-only
+        view into the parsed image's own memory (valid until close())."""
         p, n, dt = C.c_void_p(), C.c_int64(), C.c_int32()
         if lib().jxlf_array(self._h, frame, name.encode(), index, C.byref(p), C.byref(n), C.byref(dt)) != 0:
             raise KeyError("%s[%d] of frame %d" % (name, index, frame))
@@ -101,18 +102,20 @@ class ParsedImage:
         if n.value == 0:
             a = np.zeros(0, dtype)
         else:
-            a = np.frombuffer((C.c_char * (n.value * dtype.itemsize)).from_address(p.value), dtype=dtype).copy()
+            a = np.frombuffer((C.c_char * (n.value * dtype.itemsize)).from_address(p.value), dtype=dtype)
+            a = a.copy() if copy else a
         return a.reshape(shape) if shape is not None else a
 
-    def vardct_state(self, frame):
-        """The dict jxlatte_b200.host.Reconstructor.reconstruct() takes, for a VarDCT frame."""
+    def vardct_state(self, frame, copy=True):
+        """The dict jxlatte_b200.host.Reconstructor.reconstruct() takes, for a VarDCT frame.  copy=False hands out views
+        into the parsed image (no 12 B/px memcpy); they die with close()."""
         f = self.frames[frame]
         H, W = f["padded_height"], f["padded_width"]
         sx, sy = f["shift_x"], f["shift_y"]
         st = {"width": W, "height": H}
-        st["qcoeff"] = [self.array(frame, "qcoeff", c, (H >> sy[c], W >> sx[c])) for c in range(3)]
-        st["lf"] = [self.array(frame, "lf", c, ((H // 8) >> sy[c], (W // 8) >> sx[c])) for c in range(3)]
-        if not any(sx) and not any(sy):
+        st["qcoeff"] = [self.array(frame, "qcoeff", c, (H >> sy[c], W >> sx[c]), copy) for c in range(3)]
+        st["lf"] = [self.array(frame, "lf", c, ((H // 8) >> sy[c], (W // 8) >> sx[c]), copy) for c in range(3)]
+        if copy and not any(sx) and not any(sy):
             st["qcoeff"] = np.stack(st["qcoeff"])
             st["lf"] = np.stack(st["lf"])
         for k, shp in (("dct_select", (H // 8, W // 8)), ("block_origin", (H // 8, W // 8)), ("hf_mul", (H // 8, W // 8)),

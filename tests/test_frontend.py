@@ -339,3 +339,61 @@ def test_permuted_toc_crafted_from_lenna():
     a, b = base.vardct_state(0), got.vardct_state(0)
     for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y"):
         assert np.array_equal(a[k], b[k]), k
+
+
+class _FakeParsed:
+    """A ParsedImage stand-in assembled from real parsed data, to drive decoder paths no sample file reaches."""
+
+    def __init__(self, info, states, modulars):
+        self.info, self._states, self._mod = info, states, modulars
+
+    @property
+    def frames(self):
+        return self.info["frames"]
+
+    def vardct_state(self, k, copy=True):
+        return dict(self._states[k])
+
+    def modular_channels(self, k):
+        return self._mod[k]
+
+    def array(self, *a, **kw):
+        raise KeyError(a)
+
+    def close(self):
+        pass
+
+
+def test_lf_frame_and_lossy_modular_paths(monkeypatch):
+    """LF frames and XYB-encoded Modular frames occur in no sample.  Build the pair from lenna: frame 0 = an LF frame
+    (type 1, lf_level 1) coded as a lossy Modular frame whose integer Y, X, B-Y channels are lenna's own LF planes quantised
+    finely; frame 1 = lenna with USE_LF_FRAME set and empty LF planes.  The decode must come out within the LF quantisation
+    step of the ordinary decode."""
+    import copy
+    from oracle_engine import OracleEngine
+    from jxlatte_b200 import decoder as dec_mod
+    path = os.path.join(S, "lenna.jxl")
+    real = frontend.parse_file(path)
+    want = JXLDecoder(path, engine=OracleEngine()).decode().planes
+    st = real.vardct_state(0)
+    lf = st["lf"]                                              # X, Y, B float planes 64 x 64
+    step = np.float32(1.0 / 65536.0)
+    yq = np.rint(lf[1] / step).astype(np.int32)
+    xq = np.rint(lf[0] / step).astype(np.int32)
+    bq = np.rint(lf[2] / step).astype(np.int32) - yq
+    info = copy.deepcopy(real.info)
+    f1 = copy.deepcopy(info["frames"][0])
+    f0 = copy.deepcopy(f1)
+    f0.update(type=1, lf_level=1, encoding=1, width=64, height=64, padded_width=64, padded_height=64, gab=False, epf_iters=0,
+              lf_dequant=[float(step)] * 3, flags=0, is_last=False, save_as_reference=0, num_groups=1,
+              modular=dict(nb_meta=0, transformed=False, channels=[dict(h=64, w=64, hshift=0, vshift=0)] * 3, transforms=[]))
+    f1.update(flags=f1["flags"] | 32, modular=dict(nb_meta=0, transformed=False, channels=[], transforms=[]))
+    info["frames"] = [f0, f1]
+    st1 = dict(st)
+    st1["lf"] = np.zeros_like(lf)
+    fake = _FakeParsed(info, {1: st1}, {0: [yq, xq, bq], 1: []})
+    monkeypatch.setattr(dec_mod.frontend, "parse", lambda data, flags=0, strict=True: fake)
+    got = JXLDecoder(b"unused", engine=OracleEngine()).decode().planes
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) < 2e-3              # LF quantised to 2^-16: far below this, far above a wrong path
+    assert float(np.abs(got - want).max()) > 0.0

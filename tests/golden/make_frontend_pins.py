@@ -1,5 +1,5 @@
 """Regenerates tests/golden/frontend_pins.json from tests/golden/samples/*.jxl with the C++ front end and the oracle engine.
-Run after checking the decoded pictures by eye (tools/decode_sample.py --engine oracle --png ...)."""
+Run after checking the decoded pictures by eye (tests/tools/decode_with_oracle.py in.jxl out.png)."""
 import hashlib
 import json
 import os

@@ -1,6 +1,6 @@
 """Per-stage error of the CUDA path against the oracle (diagnostic; run on a GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from jxlatte_b200 import synth, default_frame_params
 from jxlatte_b200.host import Reconstructor, qm_generate

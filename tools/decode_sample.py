@@ -2,9 +2,9 @@
 front end + the CUDA reconstruction and writes PNG (8/16 bit) or PFM.  Prints the host front-end time (entropy decoding,
 headers) and the reconstruction time separately, as the north star asks.
 
-    python tools/decode_sample.py input.jxl [output.png|output.pfm] [--bits 8|16] [--engine cuda|oracle] [--repeat N]
+    python tools/decode_sample.py input.jxl [output.png|output.pfm] [--bits 8|16] [--repeat N]
 
---engine oracle runs the CPU restatement instead (checker; needs oracle/liborc.so)."""
+There is no CPU engine here: the checker's decode of the same file is tests/tools/decode_with_oracle.py."""
 import argparse
 import os
 import sys
@@ -12,7 +12,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
@@ -20,15 +19,10 @@ def main():
     ap.add_argument("input")
     ap.add_argument("output", nargs="?")
     ap.add_argument("--bits", type=int, default=8)
-    ap.add_argument("--engine", default="cuda", choices=["cuda", "oracle"])
     ap.add_argument("--repeat", type=int, default=1)
     a = ap.parse_args()
     from jxlatte_b200.decoder import CudaEngine, JXLDecoder
-    if a.engine == "oracle":
-        from oracle_engine import OracleEngine
-        engine = OracleEngine()
-    else:
-        engine = CudaEngine()
+    engine = CudaEngine()
     best = None
     for _ in range(a.repeat):
         d = JXLDecoder(a.input, engine=engine)
@@ -38,8 +32,8 @@ def main():
         if best is None or total < best[0]:
             best = (total, dict(d.timings))
     mp = img.width * img.height / 1e6
-    print("%s: %dx%d, %d channel(s), engine=%s: front end %.1f ms, reconstruction + glue %.1f ms, total %.1f ms (%.1f MP/s end to end)" % (
-        os.path.basename(a.input), img.width, img.height, img.planes.shape[0], a.engine, best[1]["front_end_s"] * 1e3,
+    print("%s: %dx%d, %d channel(s), engine=cuda: front end %.1f ms, reconstruction + glue %.1f ms, total %.1f ms (%.1f MP/s end to end)" % (
+        os.path.basename(a.input), img.width, img.height, img.planes.shape[0], best[1]["front_end_s"] * 1e3,
         best[1]["reconstruct_s"] * 1e3, best[0] * 1e3, mp / best[0]))
     if a.output:
         if a.output.endswith(".pfm"):

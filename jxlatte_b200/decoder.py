@@ -225,6 +225,9 @@ class JXLDecoder:
         self._own = engine is None
         self.engine = engine
         self.timings = {}
+        self._images = None
+        self._next = None
+        self._buffered = False
 
     def close(self):
         if self._own and self.engine is not None:
@@ -443,7 +446,27 @@ class JXLDecoder:
                                         (patch["h"], patch["w"]), d, frame_colors, (b[0], b[1], bool(b[2])), True)
 
     def decode(self):
-        """JXLCodestreamDecoder.decode's frame loop (:588-626) for the features this build renders."""
+        """JXLDecoder.decode(): the next displayed image -- frames are composed until one has a duration or is the last
+        (JXLCodestreamDecoder.java:588-626: `while (!header.isLast && header.duration == 0)`); None once the stream is
+        exhausted (atEnd()).  A still image yields one JXLImage; an animation one per displayed frame."""
+        self._advance()
+        self._buffered = False
+        return self._next
+
+    def atEnd(self):
+        """JXLDecoder.atEnd(): no further image in the stream."""
+        self._advance()
+        return self._next is None
+
+    def _advance(self):
+        if self._images is None:
+            self._images = self._compose()
+        if not self._buffered:
+            self._next = next(self._images, None)
+            self._buffered = True
+
+    def _compose(self):
+        """Generator over the displayed images: JXLCodestreamDecoder.decode's frame loop for the features this build renders."""
         import time
         t0 = time.perf_counter()
         parsed = frontend.parse(self.data)
@@ -529,11 +552,18 @@ class JXLDecoder:
                         self._blend_buffers(info, canvas[c], bufs, reference[src], ps, fo, ps, size, c, frame_colors, (m, a, bool(cl)), False)
             if save and not f["save_before_ct"]:
                 reference[f["save_as_reference"]] = canvas
-        self.timings["reconstruct_s"] = time.perf_counter() - t1
+            if f["is_last"] or f["duration"] != 0:
+                self.timings["reconstruct_s"] = time.perf_counter() - t1
+                yield self._finish(canvas, info, linear, copy=not f["is_last"])
+                t1 = time.perf_counter()
+        parsed.close()
+
+    @staticmethod
+    def _finish(canvas, info, linear, copy):
         o = info["orientation"]
         out = []
         for b in canvas:
-            a = b.a
+            a = b.a.copy() if copy else b.a
             if o != 1:                    # JXLCodestreamDecoder.transposeBuffer (:43-112)
                 if o == 2:
                     a = a[:, ::-1]
@@ -551,5 +581,4 @@ class JXLDecoder:
                     a = a.T[::-1, :]
                 a = np.ascontiguousarray(a)
             out.append(a)
-        parsed.close()
         return JXLImage(out, info, linear)

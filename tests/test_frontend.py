@@ -397,3 +397,13 @@ def test_lf_frame_and_lossy_modular_paths(monkeypatch):
     assert got.shape == want.shape
     assert float(np.abs(got - want).max()) < 2e-3              # LF quantised to 2^-16: far below this, far above a wrong path
     assert float(np.abs(got - want).max()) > 0.0
+
+
+def test_decode_iterates_displayed_images():
+    """JXLDecoder.decode() returns the next displayed image and None at the end (atEnd()), like the reference's API."""
+    from oracle_engine import OracleEngine
+    d = JXLDecoder(os.path.join(S, "white.jxl"), engine=OracleEngine())
+    assert not d.atEnd()
+    img = d.decode()
+    assert img is not None and (img.width, img.height) == (320, 240)
+    assert d.atEnd() and d.decode() is None

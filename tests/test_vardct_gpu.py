@@ -247,3 +247,14 @@ def test_inconsistent_block_maps_are_rejected(recon):
         with pytest.raises(InvalidBitstreamError):
             recon.invertVarDCT(p, bad)
     assert np.isfinite(recon.invertVarDCT(p, st)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H", [8, 264, 520, 776, 1032, 1288, 1544, 2056])
+def test_host_entry_slab_schedule_exact(recon, orc, H):
+    """The pipelined host entry point cuts tall frames into group-row slabs (first and last one group row high): every
+    schedule shape must give the whole-frame result."""
+    W = 72
+    p = default_frame_params(W, H, epf_iters=3)
+    st = _state(W, H, 100 + H, p, mix="small")
+    assert np.array_equal(recon.reconstruct(p, st), orc.vardct_reconstruct(p, st, nthreads=8))

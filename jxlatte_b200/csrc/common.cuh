@@ -55,6 +55,7 @@ struct K1Params {
     float qb[3];                // quantBias
     float qbn;                  // quantBiasNumerator
     float base_x, base_b, color_factor;
+    int vec;                    // coefficient and output planes are 16-byte aligned with pitches that are multiples of 4: 128-bit row accesses
 };
 
 struct DevTables {

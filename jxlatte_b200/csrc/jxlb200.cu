@@ -216,6 +216,9 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     for (int c = 0; c < 3; c++) P.qb[c] = p->quant_bias[c];
     P.qbn = p->quant_bias_numerator;
     P.base_x = p->base_corr_x; P.base_b = p->base_corr_b; P.color_factor = (float)p->color_factor;
+    P.vec = (pitch & 3) == 0 && (W & 3) == 0;
+    for (int c = 0; c < 3; c++)
+        if (((uintptr_t)q[c] | (uintptr_t)out[c]) & 15) P.vec = 0;
 
     // fan out: small | medium | four line-length classes of the big kernels (pass 0, then pass 1 once every pass 0 is done:
     // a varblock's row pass runs in the class of its width, its column pass in the class of its height)

@@ -147,19 +147,51 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
         const int nvb = min(SMALL_BATCH, S->cnt[type] - first);
         const int *it = items + S->start[type] + first;
 
-        // load + dequant + CfL: lane = (varblock, x), loop over y -> 32-byte row segments of 4 varblocks per request
-        const int x = tid & 7;
+        // load + dequant + CfL: lane = (varblock, row y): one 32-byte row of each coefficient plane and of each weight table per
+        // thread as two 128-bit loads (rows of a varblock are 32-byte aligned when the planes are; P.vec says so), instead of
+        // 48 scalar loads with their address arithmetic -- this phase, not the transform, was most of the kernel's instructions
+        const int y = tid & 7;
         for (int pass = 0; pass < 2; pass++) {
             const int vbi = (tid >> 3) + 16 * pass;
             if (vbi < nvb) {
                 const VB v = make_vb(P, it[vbi], type);
+                const int py = v.by * 8 + y, px = v.bx * 8;
+                const size_t gi = (size_t)py * P.W + px;
+                int q[3][8];
+                float w[3][8];
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
+                for (int c = 0; c < 3; c++) {
+                    const int32_t *qp = (c == 0 ? P.q[0] : (c == 1 ? P.q[1] : P.q[2])) + gi;
+                    if (P.vec) {
+                        const int4 a = __ldg(reinterpret_cast<const int4 *>(qp)), b4 = __ldg(reinterpret_cast<const int4 *>(qp) + 1);
+                        q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w; q[c][4] = b4.x; q[c][5] = b4.y; q[c][6] = b4.z; q[c][7] = b4.w;
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 8; x++) q[c][x] = __ldg(qp + x);
+                    }
+                    const float4 wa = __ldg(reinterpret_cast<const float4 *>(v.w[c] + y * 8)), wb4 = __ldg(reinterpret_cast<const float4 *>(v.w[c] + y * 8) + 1);
+                    w[c][0] = wa.x; w[c][1] = wa.y; w[c][2] = wa.z; w[c][3] = wa.w; w[c][4] = wb4.x; w[c][5] = wb4.y; w[c][6] = wb4.z; w[c][7] = wb4.w;
+                }
+                // chromaFromLuma factors of this row's 64x64 tile (dequant3 has the story of the gate)
+                const int tile_i = (py >> 6) * P.tw + (px >> 6);
+                float kX = 0.0f, kB = 0.0f;
+                if (__ldg(P.cfl_gate + tile_i) <= v.origin) {
+                    kX = __fadd_rn(P.base_x, __fdiv_rn((float)__ldg(P.xfy + tile_i), P.color_factor));
+                    kB = __fadd_rn(P.base_b, __fdiv_rn((float)__ldg(P.bfy + tile_i), P.color_factor));
+                }
+                float lf3[3] = {0.0f, 0.0f, 0.0f};
+                if (y == 0) { lf3[0] = __ldg(P.lf[0] + v.origin); lf3[1] = __ldg(P.lf[1] + v.origin); lf3[2] = __ldg(P.lf[2] + v.origin); }
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
                     float X, Y, B;
                     if (y == 0 && x == 0) {   // LLF of a 1x1 corner is the LF sample itself (scale 1)
-                        X = __ldg(P.lf[0] + v.origin); Y = __ldg(P.lf[1] + v.origin); B = __ldg(P.lf[2] + v.origin);
+                        X = lf3[0]; Y = lf3[1]; B = lf3[2];
                     } else {
-                        dequant3(P, v, y, x, X, Y, B);
+                        X = dequant_one(q[0][x], P.qb[0], P.qbn, v.sfc[0], w[0][x]);
+                        Y = dequant_one(q[1][x], P.qb[1], P.qbn, v.sfc[1], w[1][x]);
+                        B = dequant_one(q[2][x], P.qb[2], P.qbn, v.sfc[2], w[2][x]);
+                        X = __fadd_rn(X, __fmul_rn(kX, Y));
+                        B = __fadd_rn(B, __fmul_rn(kB, Y));
                     }
                     float *d = tile + (y * 8 + x) * SMALL_PITCH + vbi * 3;
                     d[0] = X; d[1] = Y; d[2] = B;
@@ -189,11 +221,23 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
             if (vbi < nvb) {
                 const int item = it[vbi];
                 const int by = item >> 16, bx = item & 0xffff;
+                const size_t o = (size_t)(by * 8 + y) * P.out_pitch + bx * 8;
+                float r[3][8];
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    const float *s = tile + (y * 8 + x) * SMALL_PITCH + vbi * 3;
-                    const size_t o = (size_t)(by * 8 + y) * P.out_pitch + bx * 8 + x;
-                    P.out[0][o] = s[0]; P.out[1][o] = s[1]; P.out[2][o] = s[2];
+                for (int x = 0; x < 8; x++) {
+                    const float *sp = tile + (y * 8 + x) * SMALL_PITCH + vbi * 3;
+                    r[0][x] = sp[0]; r[1][x] = sp[1]; r[2][x] = sp[2];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float *op = (c == 0 ? P.out[0] : (c == 1 ? P.out[1] : P.out[2])) + o;
+                    if (P.vec) {
+                        reinterpret_cast<float4 *>(op)[0] = make_float4(r[c][0], r[c][1], r[c][2], r[c][3]);
+                        reinterpret_cast<float4 *>(op)[1] = make_float4(r[c][4], r[c][5], r[c][6], r[c][7]);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 8; x++) op[x] = r[c][x];
+                    }
                 }
             }
         }

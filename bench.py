@@ -7,7 +7,9 @@ XYB->linear) on B200, with the roofline of the dominant kernel and the CPU resta
 A "step" = one pass of the hot path over one batch of synthetic post-entropy frame state.
   8k        (default) one 7680x4320 frame per GPU, mixed varblocks DCT8..DCT256+AFV, gab on, EPF 3 iterations; N GPUs
             = a batch of N frames sharded per image, no communication (weak scaling)
-  batch2048 eight 2048x2048 frames per GPU per step, EPF 1 iteration (per-image sharding, weak scaling)
+  batch2048 sixteen 2048x2048 frames per GPU per step, EPF 1 iteration (per-image sharding, weak scaling), handed over as
+            one vertically stacked batch (jxlb200_vardct_reconstruct_batch_dev: stage 1 once over the stack, stage 2 one
+            launch with a frame dimension)
   split16k  one 16384x16384 frame split by group rows over the N GPUs, 7 halo rows exchanged with NCCL (strong scaling)
 Prints ONE JSON line on rank 0.  Under torchrun one process per GPU; barrier + synchronize around the timed region,
 device time by CUDA events, max over ranks.
@@ -28,6 +30,7 @@ sys.path.insert(0, ROOT)
 BYTES_PER_PX = 24.35      # 12 coeff + 12 out + 0.1875 LF + 0.1563 maps + ~0.002
 BYTES_PER_PX_K2 = 24.13   # stage 2 alone: XYB in, linear out, sigma maps
 METRIC = "reconstructed MP/s (VarDCT dequant->XYB)"
+BATCH_FRAMES = 16         # frames per GPU per step of the batch2048 workload
 
 
 def peaks():
@@ -117,7 +120,7 @@ def run_reference(args):
 
 def workload_config(args, iters):
     names = {"8k": "synthetic 7680x4320 VarDCT frame per GPU (batch of N frames sharded per image), mixed varblocks DCT8-DCT256+AFV, gab on, EPF 3 iterations",
-             "batch2048": "8 synthetic 2048x2048 VarDCT frames per GPU per step (per-image sharding), mixed varblocks, gab on, EPF 1 iteration",
+             "batch2048": "%d synthetic 2048x2048 VarDCT frames per GPU per step (per-image sharding, one stacked batch call), mixed varblocks, gab on, EPF 1 iteration" % BATCH_FRAMES,
              "split16k": "synthetic 16384x16384 VarDCT frame split by group rows over N GPUs, NCCL halo rows, mixed varblocks, gab on, EPF 3 iterations"}
     return {"workload": names[args.workload], "epf_iters": iters, "parallelism": "per-image shard x%d" % args.gpus if args.workload != "split16k" else "group-row split x%d" % args.gpus,
             "l2": "inputs per step exceed the 126 MB L2 (no flush needed)"}
@@ -141,7 +144,7 @@ def run_ours(args):
     if args.workload == "8k":
         W, H, nframes = 7680, 4320, 1
     elif args.workload == "batch2048":
-        W, H, nframes = 2048, 2048, 8
+        W, H, nframes = 2048, 2048, BATCH_FRAMES
     else:
         W, H, nframes = 16384, 16384, 1
 
@@ -174,6 +177,16 @@ def run_ours(args):
         d["out"] = torch.empty((3, stf["height"], W), dtype=torch.float32, device=dev)
         frames.append(d)
 
+    stack = None
+    if nframes > 1:
+        # the batch entry point takes the frames stacked vertically in every array
+        stack = {k: torch.cat([d[k] for d in frames], dim=-2).contiguous() for k in
+                 ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
+        stack["out"] = torch.empty((3, H * nframes, W), dtype=torch.float32, device=dev)
+        for d in frames[1:]:
+            d.clear()
+        frames[0]["out"] = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+
     halo = None
     if args.workload == "split16k":
         from jxlatte_b200.multigpu import SplitFrame
@@ -182,6 +195,13 @@ def run_ours(args):
     def step():
         if halo is not None:
             halo.step()
+            return
+        if stack is not None:
+            d = stack
+            rec.reconstruct_batch_dev(p, nframes, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
+                                      d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
+                                      d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
+                                      [d["out"][c].data_ptr() for c in range(3)])
             return
         for d in frames:
             rec.reconstruct_dev(p, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],

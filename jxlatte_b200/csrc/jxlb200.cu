@@ -178,7 +178,7 @@ bool is_subsampled(const jxlb200_frame_params *p) {
 // stage 1 on device pointers
 int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *const q[3], const float *const lf[3],
                const uint8_t *ds, const uint8_t *bo, const int32_t *hf_mul, const int32_t *xfy, const int32_t *bfy,
-               float *const out[3], long long pitch, bool fanout = true) {
+               float *const out[3], long long pitch, bool fanout = true, int frame_rows = 0) {
     if (is_subsampled(p)) return ctx->fail(JXLB200_E_UNSUPPORTED, "stage 1 alone does not take chroma-subsampled frames: use jxlb200_vardct_reconstruct[_dev]");
     if (!ctx->have_weights) return ctx->fail(JXLB200_E_ARG, "jxlb200_set_qm_weights has not been called");
     const int W = p->width, H = p->height, wb = W >> 3, hb = H >> 3, tw = (W + 63) >> 6, th = (H + 63) >> 6;
@@ -194,10 +194,11 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     CUDA_TRY(ctx, cudaMemsetAsync(S, 0, sizeof(Sched), st));
     const int ncells = wb * hb;
     const int g0 = min(ctx->sms * 4, ceil_div(ncells, 256));
-    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, wb, hb, S, ctx->flags.as<int>() + 2);
+    const int fhb = frame_rows > 0 ? frame_rows >> 3 : hb;      // block rows of one frame (a batch is a vertical stack)
+    k0_count<<<g0, 256, 0, st>>>(ds, bo, ncells, wb, fhb, S, ctx->flags.as<int>() + 2);
     k0_plan<<<1, 32, 0, st>>>(S);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->gate.p, 0x7f, sizeof(int) * (size_t)tw * th, st));
-    k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, S, ctx->items.as<int>(), ctx->gate.as<int>(), tw);
+    k0_scatter<<<g0, 256, 0, st>>>(ds, bo, hb, wb, fhb, S, ctx->items.as<int>(), ctx->gate.as<int>(), tw);
     ctx->launches += 3;
 
     K1Params P;
@@ -339,7 +340,8 @@ void fill_k2(K2Params &K, const jxlb200_frame_params *p, const jxlb200_slab *sla
 
 // stage 2 on device pointers
 int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_slab *slab, const float *const xyb[3],
-                long long pitch, const int32_t *hf_mul, const int32_t *sharp, float *const out[3]) {
+                long long pitch, const int32_t *hf_mul, const int32_t *sharp, float *const out[3], int n_frames = 1) {
+    // n_frames > 1 (no slab, pitch == width, default stage 2 only): that many frames of p->height rows stacked vertically
     K2Params K;
     fill_k2(K, p, slab);
     const int W = K.W, rows = K.rows, wb = K.wb;
@@ -353,7 +355,7 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
     // inverse sigma per block, with one extra block row towards each neighbour slab
     float *inv_sigma = nullptr;
     if (K.iters > 0) {
-        CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * (rows / 8 + 2)));
+        CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * ((size_t)(rows / 8) * n_frames + 2)));
         CUDA_TRY(ctx, ctx->lut8.ensure(sizeof(float) * 8));
         if (!ctx->flags.p) {
             CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
@@ -361,17 +363,18 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->lut8.p, K.sharp_lut, sizeof(float) * 8, cudaMemcpyHostToDevice, st));
         inv_sigma = ctx->sigma.as<float>() + wb;
-        const int br0 = K.has_top ? -1 : 0, br1 = rows / 8 + (K.has_bottom ? 1 : 0);
+        const int br0 = K.has_top ? -1 : 0, br1 = (rows / 8) * n_frames + (K.has_bottom ? 1 : 0);
         k2_sigma<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(hf_mul, sharp, wb, br0, br1, K.gscale,
                                                                                      ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
     if (ctx->opt_stage2 == 0 && k2_exact_supported(K)) {          // default: fused, bit-exact
-        k2_exact_dispatch(K, inv_sigma, st);
+        k2_exact_dispatch(K, inv_sigma, st, n_frames);
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
         return 0;
     }
+    if (n_frames > 1) return ctx->fail(JXLB200_E_ARG, "stacked frames go through the default stage 2 only");
     if (ctx->opt_stage2 == 2) {                                     // opt-in: fused with re-associated EPF sums
         if (!k2_fused_supported(K)) return ctx->fail(JXLB200_E_UNSUPPORTED, "fused stage 2 does not take this frame");
         k2_fused_dispatch(K, inv_sigma, st);
@@ -675,6 +678,47 @@ int32_t jxlb200_vardct_reconstruct_dev(jxlb200_ctx *ctx, const jxlb200_frame_par
                           : invert_dev(ctx, p, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, p->width);
     if (rc) return rc;
     return restore_dev(ctx, p, nullptr, mid, p->width, hf_mul, sharpness, out);
+}
+
+// A batch of equally sized frames stacked vertically in every array (frame f occupies rows [f * H, (f + 1) * H) of the planes
+// and the matching rows of the block / tile maps; H a multiple of 64 so the 64x64 chroma-from-luma tiles of different frames do
+// not mix).  Varblocks never leave their frame, so stage 1 runs ONCE over the stack -- one set of work lists and launches, which
+// is what small frames need to fill the GPU -- and stage 2 runs per frame, each mirroring at its own edges.
+int32_t jxlb200_vardct_reconstruct_batch_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, int32_t n_frames,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (n_frames < 1) return ctx->fail(JXLB200_E_ARG, "n_frames < 1");
+    if (is_subsampled(p)) return ctx->fail(JXLB200_E_UNSUPPORTED, "batched reconstruction of chroma-subsampled frames");
+    if (p->height & 63) return ctx->fail(JXLB200_E_ARG, "batched frames need a padded height that is a multiple of 64");
+    if ((long long)p->height * n_frames > 65535ll * 8) return ctx->fail(JXLB200_E_ARG, "batch too tall");
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !out || (p->epf_iters > 0 && !sharpness))
+        return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int W = p->width, H = p->height, wb = W >> 3;
+    const size_t plane = (size_t)W * H * n_frames;
+    CUDA_TRY(ctx, ctx->mid.ensure(sizeof(float) * 3 * plane));
+    float *mid[3] = {ctx->mid.as<float>(), ctx->mid.as<float>() + plane, ctx->mid.as<float>() + 2 * plane};
+    jxlb200_frame_params ps = *p;
+    ps.height = H * n_frames;
+    rc = invert_dev(ctx, &ps, qcoeff, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, mid, W, true, H);
+    if (rc) return rc;
+    K2Params K;
+    fill_k2(K, p, nullptr);
+    if (ctx->opt_stage2 == 0 && k2_exact_supported(K)) {   // one launch, blockIdx.z = frame
+        const float *m3[3] = {mid[0], mid[1], mid[2]};
+        return restore_dev(ctx, p, nullptr, m3, W, hf_mul, sharpness, out, n_frames);
+    }
+    for (int f = 0; f < n_frames; f++) {
+        const size_t po = (size_t)f * H * W, bo_ = (size_t)f * (H >> 3) * wb;
+        const float *m3[3] = {mid[0] + po, mid[1] + po, mid[2] + po};
+        float *o3[3] = {out[0] + po, out[1] + po, out[2] + po};
+        rc = restore_dev(ctx, p, nullptr, m3, W, hf_mul + bo_, sharpness ? sharpness + bo_ : nullptr, o3);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // host-buffer entry points ------------------------------------------------------------------------------------

@@ -19,9 +19,10 @@ static const int h_big_types[2][N_BIGC][3] = {
 
 // a varblock must stay inside the frame and inside its 256x256 group (HFMetadata.placeBlock can place nothing else); the
 // kernels trust this, so a caller's inconsistent maps are rejected here instead of being written out of bounds
+// hb = block rows of ONE frame: a batch of equally sized frames may be stacked vertically (block row by = frame * hb + local row)
 __device__ __forceinline__ bool k0_valid_origin(int t, int i, int wb, int hb) {
     const TTInfo tt = c_tt[t];
-    const int by = i / wb, bx = i - by * wb;
+    const int by = (i / wb) % hb, bx = i % wb;
     return bx + tt.bw <= wb && by + tt.bh <= hb && (by & 31) + tt.bh <= 32 && (bx & 31) + tt.bw <= 32;
 }
 
@@ -79,13 +80,13 @@ __global__ void k0_plan(Sched *s) {
 // items[start[t] + i] = (by << 16) | bx of the i-th varblock of type t (order within a type is arbitrary)
 // Also fills the CfL gate: gate[tile] = raster index (by * wb + bx) of the origin of the varblock that covers the tile's
 // top-left cell (tiles are 8x8 cells); the gate array is preset to 0x7f7f7f7f ("never visited").
-__global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int hb, int wb, Sched *s,
+__global__ void k0_scatter(const uint8_t *__restrict__ ds, const uint8_t *__restrict__ bo, int hb_all, int wb, int hb, Sched *s,
                            int *__restrict__ items, int *__restrict__ gate, int tw) {
     __shared__ int h[27];
     __shared__ int base[27];
     if (threadIdx.x < 27) h[threadIdx.x] = 0;
     __syncthreads();
-    const int ncells = hb * wb;
+    const int ncells = hb_all * wb;
     const int per = (ncells + gridDim.x - 1) / gridDim.x;
     const int lo = blockIdx.x * per, hi = min(ncells, lo + per);
     // two sweeps over this CTA's cell range: count, reserve one range per type, then place

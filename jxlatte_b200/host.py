@@ -212,6 +212,12 @@ class Reconstructor:
         self._check(self._L.jxlb200_vardct_reconstruct_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf, sh,
                                                            _lib.planes(out)))
 
+    def reconstruct_batch_dev(self, p, n_frames, q, lf, ds, bo, hm, xf, bf, sh, out):
+        """n_frames equally sized frames stacked vertically in every array (p describes ONE frame, height % 64 == 0):
+        stage 1 runs once over the stack, stage 2 once per frame."""
+        self._check(self._L.jxlb200_vardct_reconstruct_batch_dev(self._h, C.byref(p), int(n_frames), _lib.planes(q), _lib.planes(lf),
+                                                                 ds, bo, hm, xf, bf, sh, _lib.planes(out)))
+
     def invert_dev(self, p, q, lf, ds, bo, hm, xf, bf, xyb, pitch):
         self._check(self._L.jxlb200_vardct_invert_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf,
                                                       _lib.planes(xyb), int(pitch)))

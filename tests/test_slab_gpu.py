@@ -66,3 +66,36 @@ def test_slabs_match_whole_frame(recon, cfg, stage2):
     finally:
         recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
     assert np.array_equal(got, whole), "max abs diff %g" % np.abs(got - whole).max()
+
+
+@pytest.mark.parametrize("cfg", [dict(W=512, H=256, n=3, iters=1, gab=True), dict(W=264, H=320, n=4, iters=3, gab=True),
+                                 dict(W=256, H=64, n=5, iters=2, gab=False), dict(W=384, H=512, n=1, iters=0, gab=True)])
+def test_batch_of_stacked_frames_matches_single_frames(recon, orc, cfg):
+    """jxlb200_vardct_reconstruct_batch_dev: n equally sized frames stacked vertically, stage 1 once over the stack, stage 2
+    per frame.  Every frame must equal its own reconstruction (oracle for frame 0, the single-frame CUDA call for all): a
+    varblock, chroma-from-luma tile or filter tap leaking across a frame boundary would show."""
+    import torch
+    W, H, n = cfg["W"], cfg["H"], cfg["n"]
+    p = default_frame_params(W, H, epf_iters=cfg["iters"], gab=cfg["gab"])
+    qw, qo = qm_generate()
+    sts = [synth.make_state(W, H, seed=900 + 7 * f + W, params=p, qm_weights=qw, qm_offsets=qo) for f in range(n)]
+    singles = [recon.reconstruct(p, s) for s in sts]
+    assert np.array_equal(singles[0], orc.vardct_reconstruct(p, sts[0], nthreads=8))
+    dev = torch.device("cuda", 0)
+    keys = ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")
+    d = {k: torch.from_numpy(np.ascontiguousarray(np.concatenate([s[k] for s in sts], axis=-2))).to(dev) for k in keys}
+    out = torch.full((3, H * n, W), np.nan, dtype=torch.float32, device=dev)
+    recon.reconstruct_batch_dev(p, n, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
+                                d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
+                                d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
+                                [out[c].data_ptr() for c in range(3)])
+    recon.sync()
+    got = out.cpu().numpy()
+    for f in range(n):
+        assert np.array_equal(got[:, f * H:(f + 1) * H], singles[f]), "frame %d of the stack differs" % f
+
+
+def test_batch_rejects_bad_shapes(recon):
+    p = default_frame_params(64, 72)        # height not a multiple of 64: chroma-from-luma tiles of two frames would mix
+    with pytest.raises(ValueError):
+        recon.reconstruct_batch_dev(p, 2, [0, 0, 0], [0, 0, 0], 0, 0, 0, 0, 0, 0, [0, 0, 0])

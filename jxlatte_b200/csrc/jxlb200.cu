@@ -164,7 +164,13 @@ int check_params(jxlb200_ctx *ctx, const jxlb200_frame_params *p) {
 
 template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, int cls, cudaStream_t st) {
     using Cfg = BigCfg<N, PASS>;
-    const int per_sm = max(1, min(min(2048 / Cfg::kThreads, 16), (227 * 1024) / (Cfg::kBytes + 1024)));
+    // persistent grid = exactly the CTAs that are resident at once (registers included: asked of the runtime, once)
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k1_big<N, PASS>, Cfg::kThreads, Cfg::kBytes) != cudaSuccess || n < 1) n = 1;
+        per_sm = min(n, 16);
+    }
     k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, st>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
     ctx->launches++;
 }

@@ -329,15 +329,15 @@ __global__ void __launch_bounds__(256) k1_medium(K1Params P, const Sched *__rest
 // N = line length.  Both passes evaluate MathHelper.inverseDCTHorizontal's recurrence
 //   out[k] = in[0] + sum_n fl(in[n] * lut[n-1][k])   in n order,
 // forming each product once for out[k] and out[N-1-k] (the float table is exactly (anti)symmetric).
-//   PASS 0  lane = column.  A warp owns outputs k0..k0+7 and their mirrors of 32 columns.  Coefficient rows that are
-//           zero on all 32 columns are dropped up front (adding +-0 products changes nothing and most rows are zero):
-//           the load phase flags live rows, a compaction builds the list, and the walk over the list reads in[n] from
-//           shared memory and lut[n-1][k0..k0+7] as two warp-uniform 128-bit loads issued one live row ahead.
-//           X and B items also dequantise Y (chroma-from-luma needs it).  Results go straight to the plane.
+//   PASS 0  load phase: lane = column, a warp per coefficient row (coalesced; X and B items also dequantise Y, which
+//           chroma-from-luma needs).  Walk: one column per warp, lanes = outputs k and their mirrors, over the column's
+//           NON-ZERO coefficients only (ballot + ffs; adding a +-0 product changes no sum and ~95 % are zero): per live n
+//           one shuffle for in[n] and one coalesced table-row read per 32 k.  Outputs replace the column in shared
+//           memory and leave as 128-byte rows.
 //   PASS 1  lane = output index k (and its mirror).  A warp owns 32 k's of 16 rows: per n one coalesced table load
 //           (issued four n ahead) and four 128-bit shared-memory broadcasts of in[row][n]; results go straight to the
 //           plane, 128 bytes per row.
-// Shared memory per CTA: PASS 0  A float[N][33] + llf scratch float[32][33] + row flags;  PASS 1  A float[N][36].
+// Shared memory per CTA: PASS 0  A float[N][33] + llf scratch float[32][33];  PASS 1  A float[N][36].
 // ------------------------------------------------------------------------------------------------------------
 #define BIG_PITCH 33
 #define BIG_PITCH1 36
@@ -345,6 +345,8 @@ template <int N, int PASS> struct BigCfg {
     static constexpr int kThreads = N == 32 ? 128 : (PASS == 0 ? 2 * N : N);
     static constexpr int kFloats = PASS == 0 ? N * BIG_PITCH + 32 * BIG_PITCH + N / 4 + 4 : (N == 32 ? N * BIG_PITCH : N * BIG_PITCH1);
     static constexpr int kBytes = kFloats * 4;
+    // the column pass is latency-bound: resident warps matter more than registers per thread (48 warps per SM = 42 registers)
+    static constexpr int kMinBlocks = N == 32 ? 6 : (PASS == 0 ? 1536 / kThreads : (N == 64 ? 14 : 1024 / kThreads));
 };
 __host__ __device__ constexpr int cos_big_off(int n) { return n == 64 ? 0 : n == 128 ? 63 * 64 : 63 * 64 + 127 * 128; }
 #define COS_BIG_FLOATS (63 * 64 + 127 * 128 + 255 * 256)
@@ -392,14 +394,11 @@ __device__ __forceinline__ float dequant_ch(const K1Params &P, const VB &v, cons
     return __fadd_rn(C, __fmul_rn(f, Y));
 }
 
-template <int N, int PASS> __global__ void __launch_bounds__(BigCfg<N, PASS>::kThreads)
+template <int N, int PASS> __global__ void __launch_bounds__(BigCfg<N, PASS>::kThreads, BigCfg<N, PASS>::kMinBlocks)
 k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
     extern __shared__ float smem[];
     float *A = smem;
     float *scr = smem + N * BIG_PITCH;   // PASS 0 only
-    unsigned char *rowflag = reinterpret_cast<unsigned char *>(scr + 32 * BIG_PITCH);
-    unsigned char *rowlist = reinterpret_cast<unsigned char *>(scr);   // valid once the LLF scratch is dead
-    int *rowcnt = reinterpret_cast<int *>(rowflag + N);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int total = S->big_cum[PASS][cls][3];
@@ -419,13 +418,50 @@ k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, i
 
         if (PASS == 0) {
             // rows i = 0..N-1 of 32 columns: coalesced 128-byte reads of the coefficient plane(s)
-            for (int i = warp; i < N; i += nwarps) {
-                const int lx = strip * 32 + lane;
-                const float val = (i < v.dsH && lx < v.dsW) ? 0.0f : dequant_ch(P, v, kc, i, lx);
-                A[i * BIG_PITCH + lane] = val;
-                if (N > 32) {
-                    const unsigned f = __ballot_sync(0xffffffffu, val != 0.0f);
-                    if (lane == 0) rowflag[i] = f != 0u;
+            // in batches of four rows so that up to sixteen loads per lane are in flight (the kernel is latency-bound: a strip is
+            // only 8-32 KB); the coefficient planes are read once (streaming loads, they must not evict the cosine table from
+            // L1), and the chroma-from-luma factor is recomputed only when the lane's 64x64 tile changes
+            {
+                const int lx = strip * 32 + lane, px = X0 + lx;
+                int last_tile = -1;
+                float f = 0.0f;
+                for (int i0 = warp; i0 < N; i0 += 4 * nwarps) {
+                    int qy[4], qc[4];
+                    float wy[4], wc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * nwarps;
+                        qy[u] = 0; qc[u] = 0; wy[u] = 0.0f; wc[u] = 0.0f;
+                        if (i < N && !(i < v.dsH && lx < v.dsW)) {
+                            const size_t gi = (size_t)(Y0 + i) * P.W + px;
+                            const int wi = i * v.W + lx;
+                            qy[u] = __ldcs(kc.qy + gi);
+                            wy[u] = __ldg(kc.wy + wi);
+                            if (c != 1) { qc[u] = __ldcs(kc.qc + gi); wc[u] = __ldg(kc.wc + wi); }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * nwarps;
+                        if (i >= N) break;
+                        float val = 0.0f;
+                        if (!(i < v.dsH && lx < v.dsW)) {
+                            const float Y = dequant_one(qy[u], kc.qb_y, P.qbn, kc.sfc_y, wy[u]);
+                            if (c == 1) {
+                                val = Y;
+                            } else {
+                                const float C = dequant_one(qc[u], kc.qb_c, P.qbn, kc.sfc_c, wc[u]);
+                                const int tile = ((Y0 + i) >> 6) * P.tw + (px >> 6);
+                                if (tile != last_tile) {      // chromaFromLuma :172-188, see dequant3 for the gate
+                                    last_tile = tile;
+                                    f = 0.0f;
+                                    if (__ldg(P.cfl_gate + tile) <= v.origin) f = __fadd_rn(kc.base, __fdiv_rn((float)__ldg(kc.fy + tile), P.color_factor));
+                                }
+                                val = __fadd_rn(C, __fmul_rn(f, Y));
+                            }
+                        }
+                        A[i * BIG_PITCH + lane] = val;
+                    }
                 }
             }
             if (strip == 0) {
@@ -462,21 +498,6 @@ k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, i
                     d2 = __fmul_rn(d2, invH);
                     const float sc = __fmul_rn(c_llf_scale[ky << (5 - lh)], c_llf_scale[kx << (5 - lw)]);
                     A[ky * BIG_PITCH + kx] = __fmul_rn(d2, sc);
-                    if (N > 32) rowflag[ky] = 1;      // LLF rows are live
-                }
-            }
-            if (N > 32) {
-                __syncthreads();
-                if (warp == 0) {                                 // compact the live rows n >= 1 (n <= 255: a byte each)
-                    int count = 0;
-                    for (int base = 1; base < N; base += 32) {
-                        const int n = base + lane;
-                        const bool f = n < N && rowflag[n] != 0;
-                        const unsigned mk = __ballot_sync(0xffffffffu, f);
-                        if (f) rowlist[count + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)n;
-                        count += __popc(mk);
-                    }
-                    if (lane == 0) rowcnt[0] = count;
                 }
             }
         } else {
@@ -511,52 +532,63 @@ k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, i
                 }
             }
         } else if (PASS == 0) {
+            // Sparse walk, one column of the strip per warp: lane l holds in[32 q + l] of chunk q, a ballot gives the column's
+            // live n (most coefficients are zero and a +-0 product changes no sum), and for each live n -- in n order -- the
+            // lanes own the outputs k = 32 m + lane and their mirrors: one coalesced table row read per 32 k, one shuffle for
+            // in[n].  Work is proportional to the non-zeros of the column, not to the rows that are live anywhere in the strip.
             const float *__restrict__ lut = P.cos_big + cos_big_off(N);
-            for (int w = warp; w < N / 16; w += nwarps) {
-                const int k0 = w * 8;
-                const float *src = A + lane;
-                const unsigned char *lst = rowlist;
-                const int cnt = rowcnt[0];
-                float lo[8], hi[8], la[8], lb[8];
-                const float in0 = src[0];
+            constexpr int KCH = N >= 64 ? N / 64 : 1, NCH = N / 32;
+            for (int j = warp; j < 32; j += nwarps) {
+                float vr[NCH];
+                unsigned mk[NCH];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { lo[q] = in0; hi[q] = in0; }
-                auto step = [&](int n, const float (&l)[8]) {
-                    const float s2 = src[n * BIG_PITCH];
-                    if (n & 1) {
+                for (int q = 0; q < NCH; q++) {
+                    vr[q] = A[(32 * q + lane) * BIG_PITCH + j];
+                    mk[q] = __ballot_sync(0xffffffffu, vr[q] != 0.0f);
+                }
+                mk[0] &= ~1u;                                   // n = 0 is the start value of every sum
+                const float in0 = __shfl_sync(0xffffffffu, vr[0], 0);
+                float lo[KCH], hi[KCH];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float p = __fmul_rn(s2, l[q]);
-                            lo[q] = __fadd_rn(lo[q], p);
-                            hi[q] = __fsub_rn(hi[q], p);
-                        }
-                    } else {
+                for (int m = 0; m < KCH; m++) { lo[m] = in0; hi[m] = in0; }
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float p = __fmul_rn(s2, l[q]);
-                            lo[q] = __fadd_rn(lo[q], p);
-                            hi[q] = __fadd_rn(hi[q], p);
+                for (int q = 0; q < NCH; q++) {
+                    unsigned m = mk[q];
+                    while (m) {                                 // warp-uniform
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float s2 = __shfl_sync(0xffffffffu, vr[q], b);
+                        const float *row = lut + (32 * q + b - 1) * N + lane;
+                        float l[KCH];
+#pragma unroll
+                        for (int u = 0; u < KCH; u++) l[u] = __ldg(row + 32 * u);
+                        if (b & 1) {                            // n odd: the mirrored table entry is the negative
+#pragma unroll
+                            for (int u = 0; u < KCH; u++) {
+                                const float pr = __fmul_rn(s2, l[u]);
+                                lo[u] = __fadd_rn(lo[u], pr);
+                                hi[u] = __fsub_rn(hi[u], pr);
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < KCH; u++) {
+                                const float pr = __fmul_rn(s2, l[u]);
+                                lo[u] = __fadd_rn(lo[u], pr);
+                                hi[u] = __fadd_rn(hi[u], pr);
+                            }
                         }
                     }
-                };
-                int na = cnt > 0 ? lst[0] : 1;
-                if (cnt > 0) ld_lut8(lut + (na - 1) * N + k0, la);
-#pragma unroll 1
-                for (int idx = 0; idx < cnt; idx += 2) {
-                    const int nb = idx + 1 < cnt ? lst[idx + 1] : 1;
-                    if (idx + 1 < cnt) ld_lut8(lut + (nb - 1) * N + k0, lb);     // one live row ahead
-                    step(na, la);
-                    if (idx + 1 >= cnt) break;
-                    na = idx + 2 < cnt ? lst[idx + 2] : 1;
-                    if (idx + 2 < cnt) ld_lut8(lut + (na - 1) * N + k0, la);
-                    step(nb, lb);
                 }
+                // column j of A belongs to this warp alone and has been read: it becomes the output column
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    plane[(size_t)(Y0 + k0 + q) * P.out_pitch + X0 + strip * 32 + lane] = lo[q];
-                    plane[(size_t)(Y0 + N - 1 - k0 - q) * P.out_pitch + X0 + strip * 32 + lane] = hi[q];
+                for (int u = 0; u < KCH; u++) {
+                    A[(32 * u + lane) * BIG_PITCH + j] = lo[u];
+                    A[(N - 1 - 32 * u - lane) * BIG_PITCH + j] = hi[u];
                 }
             }
+            __syncthreads();
+            for (int i = warp; i < N; i += nwarps)             // 128 bytes per row
+                plane[(size_t)(Y0 + i) * P.out_pitch + X0 + strip * 32 + lane] = A[i * BIG_PITCH + lane];
         } else {
             const float *__restrict__ lut = P.cos_big + cos_big_off(N);
             constexpr int KCH = N / 64;                 // 32-lane chunks of k in [0, N/2)

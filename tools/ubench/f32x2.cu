@@ -6,6 +6,9 @@ template <int MODE> __global__ void k(float *out, float a, float b) {
     float2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = make_float2(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f - i);
+    unsigned xi[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) xi[i] = threadIdx.x * 7 + i;
     const float2 A = make_float2(a, a * 1.0001f), B = make_float2(b, b * 0.9999f);
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
@@ -18,11 +21,14 @@ template <int MODE> __global__ void k(float *out, float a, float b) {
             if (MODE == 5) { v[i] = __ffma2_rn(v[i], B, A); }
             if (MODE == 6) { v[i].x = __fadd_rn(__fmul_rn(v[i].x, B.x), A.x); v[i].y = __fadd_rn(__fmul_rn(v[i].y, B.y), A.y); }
             if (MODE == 7) { v[i] = __fadd2_rn(__fmul2_rn(v[i], B), A); }
+            // issue-slot test: the same FADD work beside 8 independent ALU instructions (LOP3 / IADD3) per 16 float adds
+            if (MODE == 8) { v[i].x = __fadd_rn(v[i].x, A.x); v[i].y = __fadd_rn(v[i].y, A.y); xi[i] = (xi[i] ^ it) + (xi[i] >> 3); }
+            if (MODE == 9) { v[i] = __fadd2_rn(v[i], A); xi[i] = (xi[i] ^ it) + (xi[i] >> 3); }
         }
     }
     float s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s += v[i].x + v[i].y;
+    for (int i = 0; i < 8; i++) s += v[i].x + v[i].y + (MODE >= 8 ? (float)xi[i] : 0.0f);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int MODE> void run(const char *name, float *d) {
@@ -39,5 +45,6 @@ int main() {
     float *d; cudaMalloc(&d, 148 * 4 * 512 * 4);
     run<0>("FADD scalar", d); run<1>("FADD2 packed", d); run<2>("FMUL scalar", d); run<3>("FMUL2 packed", d);
     run<4>("FFMA scalar", d); run<5>("FFMA2 packed", d); run<6>("FMUL+FADD scalar", d); run<7>("FMUL2+FADD2 packed", d);
+    run<8>("FADD scalar + ALU mix", d); run<9>("FADD2 packed + ALU mix", d);
     return 0;
 }

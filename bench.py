@@ -149,6 +149,9 @@ def run_ours(args):
         W, H, nframes = 16384, 16384, 1
 
     rec = Reconstructor(local)
+    if os.environ.get("JXLB200_STAGE2"):      # kernel-variant experiments (include/jxlb200.h: JXLB200_OPT_STAGE2); default 0
+        from jxlatte_b200 import _lib
+        rec.set_option(_lib.OPT_STAGE2, int(os.environ["JXLB200_STAGE2"]))
     # a real (non-legacy) stream shared by torch's events and the library's kernels: a NULL handle would mean
     # "the context's own stream" to jxlb200_set_stream and the events would time nothing
     stream = torch.cuda.Stream(device=dev)

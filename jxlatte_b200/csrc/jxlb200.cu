@@ -15,6 +15,7 @@
 #include "k2_restore.cuh"
 #include "k2_fused.cuh"
 #include "k2_exact.cuh"
+#include "k2_pair.cuh"
 #include "k3_modular.cuh"
 #include "k6_subsample.cuh"
 #include "k7_blend.cuh"
@@ -142,6 +143,7 @@ int upload_constants(jxlb200_ctx *ctx) {
     CUDA_TRY(ctx, (big_attr<128, 1>())); CUDA_TRY(ctx, (big_attr<256, 1>()));
     CUDA_TRY(ctx, k2_fused_init_all());
     CUDA_TRY(ctx, k2_exact_init_all());
+    CUDA_TRY(ctx, k2_pair_init_all());
     return 0;
 }
 
@@ -374,8 +376,9 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                      ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-    if (ctx->opt_stage2 == 0 && k2_exact_supported(K)) {          // default: fused, bit-exact
-        k2_exact_dispatch(K, inv_sigma, st, n_frames);
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3) && k2_exact_supported(K)) {   // default: fused, bit-exact
+        if (ctx->opt_stage2 == 0) k2_exact_dispatch(K, inv_sigma, st, n_frames);     // one 2x2 block per thread
+        else k2_pair_dispatch(K, inv_sigma, st, n_frames);    // two blocks per thread on packed FP32x2: same bits, measured slower
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
         return 0;
@@ -566,7 +569,7 @@ int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return JXLB200_E_ARG;
-    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 2) { ctx->opt_stage2 = value; return 0; }
+    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 3) { ctx->opt_stage2 = value; return 0; }
     if (option == JXLB200_OPT_OVERLAP_ROWS && value >= 0 && (value & 255) == 0) { ctx->opt_overlap_rows = value; return 0; }
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
@@ -713,7 +716,7 @@ int32_t jxlb200_vardct_reconstruct_batch_dev(jxlb200_ctx *ctx, const jxlb200_fra
     if (rc) return rc;
     K2Params K;
     fill_k2(K, p, nullptr);
-    if (ctx->opt_stage2 == 0 && k2_exact_supported(K)) {   // one launch, blockIdx.z = frame
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3) && k2_exact_supported(K)) {   // one launch, blockIdx.z = frame
         const float *m3[3] = {mid[0], mid[1], mid[2]};
         return restore_dev(ctx, p, nullptr, m3, W, hf_mul, sharpness, out, n_frames);
     }

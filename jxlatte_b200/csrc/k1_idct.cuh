@@ -445,7 +445,9 @@ k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, i
                         const int i = i0 + u * nwarps;
                         if (i >= N) break;
                         float val = 0.0f;
-                        if (!(i < v.dsH && lx < v.dsW)) {
+                        // both coefficients zero (most are): quant = 0, 0 * sfc * w = +0 and +0 + f * +0 = +0 whatever f's
+                        // sign; the LLF corner loaded zeros above and is filled in below.  Whole rows skip the arithmetic.
+                        if ((qy[u] | qc[u]) != 0) {
                             const float Y = dequant_one(qy[u], kc.qb_y, P.qbn, kc.sfc_y, wy[u]);
                             if (c == 1) {
                                 val = Y;

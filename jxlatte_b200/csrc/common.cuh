@@ -36,6 +36,7 @@ struct Sched {
     int small_cum[N_SMALL + 1]; // cumulative batches over h_small_types
     int med_cum[N_MED + 1];
     int big_cum[2][N_BIGC][4];  // [pass][class]: cumulative strip-items over that class's (<= 3) types
+    int ticket[2][N_BIGC];      // next work item of each k1_big launch (items differ in cost: handed out dynamically)
 };
 
 // Per-frame arguments of the stage-1 kernels

@@ -173,7 +173,8 @@ template <int N, int PASS> void launch_big(jxlb200_ctx *ctx, const K1Params &P, 
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k1_big<N, PASS>, Cfg::kThreads, Cfg::kBytes) != cudaSuccess || n < 1) n = 1;
         per_sm = min(n, 16);
     }
-    k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, st>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls);
+    k1_big<N, PASS><<<ctx->sms * per_sm, Cfg::kThreads, Cfg::kBytes, st>>>(P, ctx->sched.as<Sched>(), ctx->items.as<int>(), cls,
+                                                                                     &ctx->sched.as<Sched>()->ticket[PASS][cls]);
     ctx->launches++;
 }
 

@@ -395,14 +395,21 @@ __device__ __forceinline__ float dequant_ch(const K1Params &P, const VB &v, cons
 }
 
 template <int N, int PASS> __global__ void __launch_bounds__(BigCfg<N, PASS>::kThreads, BigCfg<N, PASS>::kMinBlocks)
-k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls) {
+k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, int cls, int *__restrict__ ticket) {
     extern __shared__ float smem[];
+    __shared__ int s_wi;
     float *A = smem;
     float *scr = smem + N * BIG_PITCH;   // PASS 0 only
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int total = S->big_cum[PASS][cls][3];
-    for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {
+    // items are handed out through a counter (zeroed with the rest of Sched before K0): a strip with an LLF corner or a dense
+    // column costs several times a sparse one, and a static round-robin left the last CTAs running alone
+    for (;;) {
+        if (tid == 0) s_wi = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int wi = s_wi;     // every thread reads it before the barrier that ends the item, after which thread 0 rewrites it
+        if (wi >= total) break;
         int j = 0;
         while (wi >= S->big_cum[PASS][cls][j + 1]) j++;
         const int type = c_big_types[PASS][cls][j];

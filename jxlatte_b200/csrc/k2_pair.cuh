@@ -33,11 +33,14 @@
 #ifndef KP_THREADS
 #define KP_THREADS 128
 #endif
+#define KP_TH 32                          /* tile height (its own: two CTAs of 102 KB share an SM) */
+#define KP_PH (KP_TH + 2 * KX_HALO)
+#define KP_NBY (KP_PH / 8)
 #define KP_SHIFT 36                       /* columns between the two blocks of a pair */
 #define KP_PJ 44                          /* pairs per padded row */
 #define KP_PWX (2 * KP_PJ)                /* floats per padded row */
-#define KP_PLANE (KX_PH * KP_PWX)
-#define KP_BYTES (2 * 3 * KP_PLANE * 4 + (KX_PH + KX_PW) * 4 + KX_NBY * KX_NBX * 4)
+#define KP_PLANE (KP_PH * KP_PWX)
+#define KP_BYTES (2 * 3 * KP_PLANE * 4 + (KP_PH + KX_PW) * 4 + KP_NBY * KX_NBX * 4)
 
 typedef unsigned long long p2;            // two floats: low = left block, high = right block
 
@@ -60,7 +63,7 @@ __device__ __forceinline__ int kp_idx2(int y, int c) {
 // After a stage wrote its in-frame outputs: out-of-frame positions take the stage's value at the mirrored coordinate (see
 // mirror_fill in k2_exact.cuh for why outputs, not inputs, are mirrored) and the second copy of columns 36..43 is refreshed.
 __device__ __forceinline__ void kp_fixup(float *buf, const KxTile &T, int margin, bool edge) {
-    const int rh = KX_TH + 2 * margin, rw = KX_TW + 2 * margin;
+    const int rh = KP_TH + 2 * margin, rw = KX_TW + 2 * margin;
     if (!edge) {
         // nothing mirrors in this tile (all but the frame's border tiles): only the eight shared columns need their copy
         for (int i = threadIdx.x; i < rh * 8; i += KP_THREADS) {
@@ -285,19 +288,19 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
     constexpr int M0 = GAB + (ITERS == 3 ? 3 : 0) + (ITERS >= 1 ? 2 : 0) + (ITERS >= 2 ? 1 : 0);
     extern __shared__ float sm[];
     float *bufA = sm, *bufB = sm + 3 * KP_PLANE;
-    int *mrow = reinterpret_cast<int *>(sm + 6 * KP_PLANE), *mcol = mrow + KX_PH;
+    int *mrow = reinterpret_cast<int *>(sm + 6 * KP_PLANE), *mcol = mrow + KP_PH;
     float *isig = reinterpret_cast<float *>(mcol + KX_PW);
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * KX_TW, ty0 = blockIdx.y * KX_TH;
+    const int tx0 = blockIdx.x * KX_TW, ty0 = blockIdx.y * KP_TH;
     KxTile T{isig, mrow, mcol};
     const long long zo = blockIdx.z * zpx;
     inv_sigma += (long long)blockIdx.z * zblk;
     const int rlo = P.has_top ? -JXLB200_HALO_ROWS : 0, rhi = P.rows - 1 + (P.has_bottom ? JXLB200_HALO_ROWS : 0);
 
-    for (int i = tid; i < KX_PH; i += KP_THREADS) {
+    for (int i = tid; i < KP_PH; i += KP_THREADS) {
         int r = mirror_row(ty0 - KX_HALO + i, P.rows, P.has_top, P.has_bottom);
         r = min(max(r, rlo), rhi);
-        mrow[i] = min(max(r - (ty0 - KX_HALO), 0), KX_PH - 1);
+        mrow[i] = min(max(r - (ty0 - KX_HALO), 0), KP_PH - 1);
     }
     for (int i = tid; i < KX_PW; i += KP_THREADS) {
         int x = mirror_col(tx0 - KX_HALO + i, P.W);
@@ -305,7 +308,7 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
         mcol[i] = min(max(x - (tx0 - KX_HALO), 0), KX_PW - 1);
     }
     if (ITERS > 0) {
-        for (int i = tid; i < KX_NBY * KX_NBX; i += KP_THREADS) {
+        for (int i = tid; i < KP_NBY * KX_NBX; i += KP_THREADS) {
             const int gy = ty0 - KX_HALO + 8 * (i / KX_NBX), gx = tx0 - KX_HALO + 8 * (i % KX_NBX);
             const bool inside = gy >= rlo && gy <= rhi && gx >= 0 && gx < P.W;
             isig[i] = inside ? __ldg(inv_sigma + (gy >> 3) * P.wb + (gx >> 3)) : __int_as_float(0x7fc00000);
@@ -313,12 +316,12 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
     }
     // raw tile -> bufA, both copies of the shared columns.  Interior tiles: a thread takes four pairs of a row = padded columns
     // [4g, 4g + 4) and [4g + 36, 4g + 40), two 128-bit global loads and two 128-bit shared stores.
-    const bool interior = tx0 >= KX_HALO && tx0 + KX_TW + KX_HALO <= P.W && ty0 - KX_HALO >= rlo && ty0 + KX_TH + KX_HALO - 1 <= rhi &&
+    const bool interior = tx0 >= KX_HALO && tx0 + KX_TW + KX_HALO <= P.W && ty0 - KX_HALO >= rlo && ty0 + KP_TH + KX_HALO - 1 <= rhi &&
                           (P.in_pitch & 3) == 0;
     if (interior) {
         constexpr int G = KP_PJ / 4;
-        for (int i = tid; i < 3 * KX_PH * G; i += KP_THREADS) {
-            const int c = i / (KX_PH * G), rem = i - c * (KX_PH * G), ly = rem / G, g = rem - ly * G;
+        for (int i = tid; i < 3 * KP_PH * G; i += KP_THREADS) {
+            const int c = i / (KP_PH * G), rem = i - c * (KP_PH * G), ly = rem / G, g = rem - ly * G;
             const float *src = P.in[c] + zo + (long long)(ty0 - KX_HALO + ly) * P.in_pitch + tx0 - KX_HALO + 4 * g;
             const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src + KP_SHIFT));
             float *dst = bufA + c * KP_PLANE + ly * KP_PWX + 8 * g;
@@ -326,7 +329,7 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
             *reinterpret_cast<float4 *>(dst + 4) = make_float4(a.z, b.z, a.w, b.w);
         }
     } else {
-        for (int i = tid; i < KX_PH * KP_PJ; i += KP_THREADS) {
+        for (int i = tid; i < KP_PH * KP_PJ; i += KP_THREADS) {
             const int ly = i / KP_PJ, j = i - ly * KP_PJ;
             int r = mirror_row(ty0 - KX_HALO + ly, P.rows, P.has_top, P.has_bottom);
             r = min(max(r, rlo), rhi);
@@ -342,13 +345,13 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
     // does anything in this padded tile mirror?  (CTA-uniform)
     __syncthreads();
     bool mirrors = false;
-    for (int i = tid; i < KX_PH + KX_PW; i += KP_THREADS) mirrors |= i < KX_PH ? mrow[i] != i : mcol[i - KX_PH] != i - KX_PH;
+    for (int i = tid; i < KP_PH + KX_PW; i += KP_THREADS) mirrors |= i < KP_PH ? mrow[i] != i : mcol[i - KP_PH] != i - KP_PH;
     const bool edge = __syncthreads_or(mirrors) != 0;
 
     float *cur = bufA, *nxt = bufB;
     if (GAB) {
         // pixel pairs j in [2, 42): left column j, right column j + 36, each stored when it lies inside margin M0 - 1 and the frame
-        constexpr int m = M0 - 1, rh = KX_TH + 2 * m, jw = 40;
+        constexpr int m = M0 - 1, rh = KP_TH + 2 * m, jw = 40;
         for (int i = tid; i < rh * jw; i += KP_THREADS) {
             const int ly = KX_HALO - m + i / jw, j = 2 + i % jw;
             const int cA = j, cB = j + KP_SHIFT;
@@ -380,7 +383,7 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
     // EPF passes over block pairs at even rows and even pair columns j in [4, 40)
 #define KP_RUN_PASS(PASS, MARGIN, LAST)                                                                                   \
     {                                                                                                                     \
-        constexpr int mm = ((MARGIN) + 1) & ~1, rh = KX_TH + 2 * mm, nb = (rh / 2) * 18;                                   \
+        constexpr int mm = ((MARGIN) + 1) & ~1, rh = KP_TH + 2 * mm, nb = (rh / 2) * 18;                                   \
         _Pragma("unroll 1") for (int b = tid; b < nb; b += KP_THREADS) {                                                  \
             const int ly = KX_HALO - mm + 2 * (b / 18), j = 4 + 2 * (b % 18);                                              \
             const int cA = j, cB = j + KP_SHIFT;                                                                          \
@@ -407,7 +410,7 @@ template <int GAB, int ITERS> __global__ void __launch_bounds__(KP_THREADS, 2) k
 #undef KP_RUN_PASS
 
     // colour transform + store: four pixels per thread, read from their primary slots, 128-bit rows out
-    for (int i = tid; i < KX_TH * (KX_TW / 4); i += KP_THREADS) {
+    for (int i = tid; i < KP_TH * (KX_TW / 4); i += KP_THREADS) {
         const int ly = KX_HALO + i / (KX_TW / 4), lx = KX_HALO + 4 * (i % (KX_TW / 4));
         const int oy = ty0 + ly - KX_HALO, ox = tx0 + lx - KX_HALO;
         if (oy >= P.rows || ox >= P.W) continue;
@@ -444,7 +447,7 @@ static inline cudaError_t k2_pair_init_all() {
     return cudaSuccess;
 }
 template <int GAB, int ITERS> static void k2_pair_go(const K2Params &K, const float *inv_sigma, cudaStream_t st, int nz, long long zpx, int zblk) {
-    const dim3 grid((K.W + KX_TW - 1) / KX_TW, (K.rows + KX_TH - 1) / KX_TH, nz);
+    const dim3 grid((K.W + KX_TW - 1) / KX_TW, (K.rows + KP_TH - 1) / KP_TH, nz);
     k2_pair<GAB, ITERS><<<grid, KP_THREADS, KP_BYTES, st>>>(K, inv_sigma, zpx, zblk);
 }
 static inline void k2_pair_dispatch(const K2Params &K, const float *inv_sigma, cudaStream_t st, int n_frames = 1) {

@@ -150,9 +150,12 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
         // load + dequant + CfL: lane = (varblock, row y): one 32-byte row of each coefficient plane and of each weight table per
         // thread as two 128-bit loads (rows of a varblock are 32-byte aligned when the planes are; P.vec says so), instead of
         // 48 scalar loads with their address arithmetic -- this phase, not the transform, was most of the kernel's instructions
-        const int y = tid & 7;
+        // lane -> (varblock, row): sixteen varblocks side by side, two rows per warp.  The staging index is (y * 8 + x) * 100 +
+        // 3 * varblock + c, so rows fall on the same bank (800 = 0 mod 32) and varblocks on distinct ones: eight rows per warp
+        // (the earlier mapping) made every staging access an 8-way bank conflict, two rows make it 2-way
+        const int y = tid >> 4;
         for (int pass = 0; pass < 2; pass++) {
-            const int vbi = (tid >> 3) + 16 * pass;
+            const int vbi = (tid & 15) + 16 * pass;
             if (vbi < nvb) {
                 const VB v = make_vb(P, it[vbi], type);
                 const int py = v.by * 8 + y, px = v.bx * 8;
@@ -175,9 +178,13 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
                 // chromaFromLuma factors of this row's 64x64 tile (dequant3 has the story of the gate)
                 const int tile_i = (py >> 6) * P.tw + (px >> 6);
                 float kX = 0.0f, kB = 0.0f;
-                if (__ldg(P.cfl_gate + tile_i) <= v.origin) {
-                    kX = __fadd_rn(P.base_x, __fdiv_rn((float)__ldg(P.xfy + tile_i), P.color_factor));
-                    kB = __fadd_rn(P.base_b, __fdiv_rn((float)__ldg(P.bfy + tile_i), P.color_factor));
+                {
+                    // the three loads leave together (one round trip instead of gate -> factors): this kernel is latency-bound
+                    const int gate = __ldg(P.cfl_gate + tile_i), fx = __ldg(P.xfy + tile_i), fb = __ldg(P.bfy + tile_i);
+                    if (gate <= v.origin) {
+                        kX = __fadd_rn(P.base_x, __fdiv_rn((float)fx, P.color_factor));
+                        kB = __fadd_rn(P.base_b, __fdiv_rn((float)fb, P.color_factor));
+                    }
                 }
                 float lf3[3] = {0.0f, 0.0f, 0.0f};
                 if (y == 0) { lf3[0] = __ldg(P.lf[0] + v.origin); lf3[1] = __ldg(P.lf[1] + v.origin); lf3[2] = __ldg(P.lf[2] + v.origin); }
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(128) k1_small(K1Params P, const Sched *__restr
         }
         __syncthreads();
         for (int pass = 0; pass < 2; pass++) {
-            const int vbi = (tid >> 3) + 16 * pass;
+            const int vbi = (tid & 15) + 16 * pass;
             if (vbi < nvb) {
                 const int item = it[vbi];
                 const int by = item >> 16, bx = item & 0xffff;
@@ -588,7 +595,9 @@ k1_big(K1Params P, const Sched *__restrict__ S, const int *__restrict__ items, i
                         }
                     }
                 }
-                // column j of A belongs to this warp alone and has been read: it becomes the output column
+                // column j of A belongs to this warp alone and has been read: it becomes the output column (other lanes read
+                // the elements this lane overwrites: the ballots ordered that in practice, __syncwarp orders it formally)
+                __syncwarp();
 #pragma unroll
                 for (int u = 0; u < KCH; u++) {
                     A[(32 * u + lane) * BIG_PITCH + j] = lo[u];

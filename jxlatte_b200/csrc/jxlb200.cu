@@ -757,7 +757,7 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 // slab needs HALO rows of the next slab's stage-1 output, hence the one-slab lag; the planes are contiguous on the
 // device, so "halo rows" are simply the neighbouring slab's rows (jxlb200_slab with has_top / has_bottom).
 #ifndef JXLB200_PIPE_ROWS
-#define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; PCIe floor (398 MB each way, duplex) 8.6 ms */
+#define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
 #endif
 int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],

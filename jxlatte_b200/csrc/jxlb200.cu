@@ -817,20 +817,22 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
         for (int c = 0; c < 3; c++)      // the LF planes are 1/64 of the coefficients: whole, up front
             CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * nb, cudaMemcpyHostToDevice, up));
     }
-    // slab schedule: one group row (256) first and last so the pipeline fills and drains quickly, JXLB200_PIPE_ROWS in between
+    // slab schedule.  Stage 2 of slab j needs stage 1 of slab j + 1, so the first download starts after TWO uploads and two
+    // downloads remain when the last upload ends: the first two and the last two slabs are one group row (256) each so that the
+    // pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS
     std::vector<int> slab_start;
     {
-        int y = 0;
-        const int edge = H > 2 * JXLB200_PIPE_ROWS ? 256 : JXLB200_PIPE_ROWS;
-        while (y < H) {
-            slab_start.push_back(y);
-            const int left = H - y;
-            int take = (y == 0) ? edge : JXLB200_PIPE_ROWS;
-            if (left - take < edge && left > edge && edge < JXLB200_PIPE_ROWS) take = left - edge > 0 ? ((left - edge + 255) / 256) * 256 : left;
-            if (take <= 0 || take > left) take = left;
-            if (left - take > 0 && left - take < 8) take = left;
-            y += take;
+        const int G = (H + 255) / 256, per = JXLB200_PIPE_ROWS / 256;     // group rows in the frame / per middle slab
+        const int edge = G >= 4 + per ? 2 : (G >= 2 + per ? 1 : 0);        // single-group-row slabs at each end
+        int g = 0;
+        while (g < G) {
+            slab_start.push_back(g * 256);
+            const int left = G - g;
+            int take = (g < edge || left <= edge) ? 1 : min(per, left - edge);
+            if (take < 1) take = 1;
+            g += take;
         }
+        // a last slab of fewer than 8 rows cannot exist (heights are multiples of 8), nothing else to fix up
     }
     const int nslab = (int)slab_start.size();
     std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);

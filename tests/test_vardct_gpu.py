@@ -252,8 +252,8 @@ def test_inconsistent_block_maps_are_rejected(recon):
 @pytest.mark.gpu
 @pytest.mark.parametrize("H", [8, 264, 520, 776, 1032, 1288, 1544, 2056])
 def test_host_entry_slab_schedule_exact(recon, orc, H):
-    """The pipelined host entry point cuts tall frames into group-row slabs (first and last one group row high): every
-    schedule shape must give the whole-frame result."""
+    """The pipelined host entry point cuts tall frames into group-row slabs (the first two and the last two one group row
+    high, 512 rows in between): every schedule shape must give the whole-frame result."""
     W = 72
     p = default_frame_params(W, H, epf_iters=3)
     st = _state(W, H, 100 + H, p, mix="small")

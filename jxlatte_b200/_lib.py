@@ -54,6 +54,7 @@ SYMBOLS = {
     "jxlb200_restore_dev": (_i32, [_vp, _FP, C.POINTER(Slab), _P3, C.c_int64, _vp, _vp, _P3]),
     "jxlb200_vardct_reconstruct_dev": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
     "jxlb200_vardct_reconstruct_batch_dev": (_i32, [_vp, _FP, _i32, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
+    "jxlb200_host_slab_schedule": (_i32, [_i32, _vp, _i32]),
     "jxlb200_gaborish": (_i32, [_vp, _FP, _P3, _P3]),
     "jxlb200_epf": (_i32, [_vp, _FP, _P3, _vp, _vp, _P3]),
     "jxlb200_color_transform": (_i32, [_vp, _FP, _P3, _P3]),

@@ -756,9 +756,34 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 // 2) -- PCIe is full duplex, so the call costs about max(upload, download, compute) instead of their sum.  Stage 2 of a
 // slab needs HALO rows of the next slab's stage-1 output, hence the one-slab lag; the planes are contiguous on the
 // device, so "halo rows" are simply the neighbouring slab's rows (jxlb200_slab with has_top / has_bottom).
+// Slab schedule of the pipelined host entry point.  Stage 2 of slab j needs stage 1 of slab j + 1, so the first download starts
+// after TWO uploads and two downloads remain when the last upload ends: the first two and the last two slabs are one group row
+// (256) each so that the pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS.
+static void host_slab_schedule(int H, std::vector<int> &slab_start);
 #ifndef JXLB200_PIPE_ROWS
 #define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
 #endif
+static void host_slab_schedule(int H, std::vector<int> &slab_start) {
+    const int G = (H + 255) / 256, per = JXLB200_PIPE_ROWS / 256;     // group rows in the frame / per middle slab
+    const int edge = G >= 4 + per ? 2 : (G >= 2 + per ? 1 : 0);        // single-group-row slabs at each end
+    int g = 0;
+    slab_start.clear();
+    while (g < G) {
+        slab_start.push_back(g * 256);
+        const int left = G - g;
+        int take = (g < edge || left <= edge) ? 1 : min(per, left - edge);
+        if (take < 1) take = 1;
+        g += take;
+    }
+}
+// the schedule, for callers that want to overlap their own work with the slabs and for the CPU tests (no device needed)
+int32_t jxlb200_host_slab_schedule(int32_t height, int32_t *starts, int32_t capacity) {
+    if (height <= 0 || (height & 7)) return JXLB200_E_ARG;
+    std::vector<int> v;
+    host_slab_schedule(height, v);
+    for (int i = 0; i < (int)v.size() && starts && i < capacity; i++) starts[i] = v[i];
+    return (int32_t)v.size();
+}
 int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
     const int32_t *const qcoeff[3], const float *const lf[3],
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
@@ -817,23 +842,8 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
         for (int c = 0; c < 3; c++)      // the LF planes are 1/64 of the coefficients: whole, up front
             CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * nb, cudaMemcpyHostToDevice, up));
     }
-    // slab schedule.  Stage 2 of slab j needs stage 1 of slab j + 1, so the first download starts after TWO uploads and two
-    // downloads remain when the last upload ends: the first two and the last two slabs are one group row (256) each so that the
-    // pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS
     std::vector<int> slab_start;
-    {
-        const int G = (H + 255) / 256, per = JXLB200_PIPE_ROWS / 256;     // group rows in the frame / per middle slab
-        const int edge = G >= 4 + per ? 2 : (G >= 2 + per ? 1 : 0);        // single-group-row slabs at each end
-        int g = 0;
-        while (g < G) {
-            slab_start.push_back(g * 256);
-            const int left = G - g;
-            int take = (g < edge || left <= edge) ? 1 : min(per, left - edge);
-            if (take < 1) take = 1;
-            g += take;
-        }
-        // a last slab of fewer than 8 rows cannot exist (heights are multiples of 8), nothing else to fix up
-    }
+    host_slab_schedule(H, slab_start);
     const int nslab = (int)slab_start.size();
     std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);
     for (int i = 0; i < nslab; i++) {

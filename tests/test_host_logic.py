@@ -49,3 +49,25 @@ def test_split_state_cuts_every_map_consistently():
     s = split_state(st, 256, 256)
     assert s["qcoeff"].shape == (3, 256, 64) and s["lf"].shape == (3, 32, 8) and s["x_from_y"].shape == (4, 1)
     assert np.array_equal(s["hf_mul"], st["hf_mul"][32:])
+
+
+def test_host_entry_slab_schedule_partitions_the_frame():
+    """jxlb200_host_slab_schedule (the pipelined host entry point's slab plan; needs no device): slabs start on group rows,
+    cover the frame once, and tall frames get two one-group-row slabs at each end so the pipeline fills and drains fast."""
+    import ctypes as C
+    from jxlatte_b200 import _lib
+    L = _lib.lib()
+    for H in (8, 64, 256, 264, 512, 776, 1032, 2048, 2056, 4320, 16384, 65536):
+        buf = (C.c_int32 * 512)()
+        n = L.jxlb200_host_slab_schedule(H, buf, 512)
+        assert n >= 1
+        starts = list(buf[:n])
+        assert starts[0] == 0 and all(s % 256 == 0 for s in starts) and starts == sorted(set(starts)) and starts[-1] < H
+        rows = [b - a for a, b in zip(starts, starts[1:] + [H])]
+        assert sum(rows) == H and all(r >= 8 and r % 8 == 0 for r in rows)
+        assert max(rows) <= 512
+        if H >= 6 * 256:
+            assert rows[0] == rows[1] == 256 and rows[-2] == 256 and rows[-1] <= 256
+    assert L.jxlb200_host_slab_schedule(4320, None, 0) == 11          # count only
+    assert L.jxlb200_host_slab_schedule(12, None, 0) == _lib.E_ARG    # heights are padded to 8
+    assert L.jxlb200_host_slab_schedule(0, None, 0) == _lib.E_ARG

@@ -61,7 +61,7 @@ struct jxlb200_ctx {
     DevBuf sched, items, gate, wraw, woff, wexp, cosbig, lut8, sigma, flags;
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
-    DevBuf in_q, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    DevBuf in_q, in_q16, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
     DevBuf blend;           // five compact rectangles of jxlb200_blend
     DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
     DevTables tab;
@@ -354,8 +354,8 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
     K2Params K;
     fill_k2(K, p, slab);
     const int W = K.W, rows = K.rows, wb = K.wb;
-    if (slab && ((slab->y0 & 255) || (slab->rows & 7) || slab->rows <= 0 || slab->y0 + slab->rows > slab->frame_height))
-        return ctx->fail(JXLB200_E_ARG, "slab must start on a group row and stay inside the frame");
+    if (slab && ((slab->y0 & 7) || (slab->rows & 7) || slab->rows <= 0 || slab->y0 + slab->rows > slab->frame_height))
+        return ctx->fail(JXLB200_E_ARG, "slab must start on a block row and stay inside the frame");
     cudaStream_t st = ctx->stream;
     for (int c = 0; c < 3; c++) { K.in[c] = xyb[c]; K.out[c] = out[c]; }
     K.in_pitch = pitch; K.out_pitch = W;
@@ -540,7 +540,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend};
     for (DevBuf *b : all) b->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -622,6 +622,7 @@ int32_t jxlb200_restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
         return ctx->fail(JXLB200_E_ARG, "NULL plane pointer or pitch < width");
     for (int c = 0; c < 3; c++)
         if (xyb[c] == out[c]) return ctx->fail(JXLB200_E_ARG, "in-place restore is not allowed");
+    if (slab && (slab->y0 & 255)) return ctx->fail(JXLB200_E_ARG, "slab must start on a group row and stay inside the frame");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return restore_dev(ctx, p, slab, xyb, xyb_pitch, hf_mul, sharpness, out);
 }
@@ -752,13 +753,15 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 }
 
 // Whole path on host buffers.  Frames taller than one slab are pipelined by group rows over three streams: while slab i
-// is uploaded (copy engine 1), stage 1 of slab i-1 and stage 2 of slab i-2 run, and slab i-3's pixels go back (copy engine
-// 2) -- PCIe is full duplex, so the call costs about max(upload, download, compute) instead of their sum.  Stage 2 of a
-// slab needs HALO rows of the next slab's stage-1 output, hence the one-slab lag; the planes are contiguous on the
-// device, so "halo rows" are simply the neighbouring slab's rows (jxlb200_slab with has_top / has_bottom).
-// Slab schedule of the pipelined host entry point.  Stage 2 of slab j needs stage 1 of slab j + 1, so the first download starts
-// after TWO uploads and two downloads remain when the last upload ends: the first two and the last two slabs are one group row
-// (256) each so that the pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS.
+// is uploaded (copy engine 1), stage 1 and stage 2 of slab i-1 run, and slab i-2's pixels go back (copy engine 2) -- PCIe
+// is full duplex, so the call costs about max(upload, download, compute) instead of their sum.  Stage 2 needs HALO rows
+// of stage-1 output below the rows it produces, so the stage-2 / download ranges are the upload slabs SHIFTED UP by
+// JXLB200_HALO_ROWS: after stage 1 of slab i = rows [s_i, s_i+1), stage 2 runs on rows [s_i - 8, s_i+1 - 8) (from 0 for the
+// first slab, to the frame's end for the last) -- everything it reads exists already, and no slab waits for the next
+// one's upload.  The planes are contiguous on the device, so "halo rows" are simply the neighbouring rows (jxlb200_slab
+// with has_top / has_bottom; the kernels only need a range to start on a block row).
+// Slab schedule of the pipelined host entry point: the first two and the last two slabs are one group row (256) each so
+// that the pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS.
 static void host_slab_schedule(int H, std::vector<int> &slab_start);
 #ifndef JXLB200_PIPE_ROWS
 #define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
@@ -784,9 +787,30 @@ int32_t jxlb200_host_slab_schedule(int32_t height, int32_t *starts, int32_t capa
     for (int i = 0; i < (int)v.size() && starts && i < capacity; i++) starts[i] = v[i];
     return (int32_t)v.size();
 }
-int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
-    const int32_t *const qcoeff[3], const float *const lf[3],
-    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+// int16 coefficients (jxlb200_vardct_reconstruct_i16) are widened on the device: 8 per thread, one 128-bit load, two
+// 128-bit stores; the few elements of a plane that is not a multiple of 8 long go through the scalar tail.
+__global__ void k9_widen_i16(const int16_t *__restrict__ in, int32_t *__restrict__ out, size_t n) {
+    const size_t n8 = n >> 3, stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < n8; i += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + i);
+        int4 lo, hi;
+        lo.x = (int)(short)(v.x & 0xffff); lo.y = v.x >> 16; lo.z = (int)(short)(v.y & 0xffff); lo.w = v.y >> 16;
+        hi.x = (int)(short)(v.z & 0xffff); hi.y = v.z >> 16; hi.z = (int)(short)(v.w & 0xffff); hi.w = v.w >> 16;
+        reinterpret_cast<int4 *>(out)[2 * i] = lo;
+        reinterpret_cast<int4 *>(out)[2 * i + 1] = hi;
+    }
+    for (size_t i = (n8 << 3) + t; i < n; i += stride) out[i] = in[i];
+}
+static void widen_i16(jxlb200_ctx *ctx, const int16_t *in, int32_t *out, size_t n, cudaStream_t st) {
+    const size_t want = ((n >> 3) + 255) / 256 + 1;
+    const int grid = (int)(want < (size_t)ctx->sms * 8 ? want : (size_t)ctx->sms * 8);
+    k9_widen_i16<<<grid, 256, 0, st>>>(in, out, n);
+    ctx->launches++;
+}
+
+// qbytes = 4: qcoeff planes are int32 (HFCoefficients.quantizedCoeffs as the reference holds them); 2: int16
+static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const void *const qcoeff[3], int qbytes,
+    const float *const lf[3], const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
     const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
     int rc = check_params(ctx, p);
     if (rc) return rc;
@@ -797,39 +821,39 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int W = p->width, H = p->height, wb = W >> 3, tw = (W + 63) >> 6;
     const size_t npx = (size_t)W * H, nb = npx / 64;
-    if (is_subsampled(p)) {
-        // chroma-subsampled frame: plain upload -> stage 1 per channel + upsampling -> stage 2 -> download
-        CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(int32_t) * npx));
-        CUDA_TRY(ctx, ctx->in_lf.ensure(3 * sizeof(float) * nb));
-        CUDA_TRY(ctx, ctx->mid.ensure(3 * sizeof(float) * npx));
-        CUDA_TRY(ctx, ctx->out_planes.ensure(3 * sizeof(float) * npx));
-        const int32_t *dq[3]; const float *dlf[3]; float *mid[3], *dout[3];
-        for (int c = 0; c < 3; c++) {
-            const size_t nc = (size_t)(W >> p->shift_x[c]) * (H >> p->shift_y[c]);
-            int32_t *qd = ctx->in_q.as<int32_t>() + c * npx;
-            float *ld = ctx->in_lf.as<float>() + c * nb;
-            CUDA_TRY(ctx, cudaMemcpyAsync(qd, qcoeff[c], sizeof(int32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(ld, lf[c], sizeof(float) * (nc / 64), cudaMemcpyHostToDevice, ctx->stream));
-            dq[c] = qd; dlf[c] = ld;
-            mid[c] = ctx->mid.as<float>() + c * npx;
-            dout[c] = ctx->out_planes.as<float>() + c * npx;
-        }
-        HostMaps M;
-        if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
-        if ((rc = invert_subsampled_dev(ctx, p, dq, dlf, M.ds, M.hf, mid))) return rc;
-        if ((rc = restore_dev(ctx, p, nullptr, mid, W, M.hf, M.sharp, dout))) return rc;
-        return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
-    }
+    const bool narrow = qbytes == 2;
     CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(int32_t) * npx));
+    if (narrow) CUDA_TRY(ctx, ctx->in_q16.ensure(3 * sizeof(int16_t) * npx));
     CUDA_TRY(ctx, ctx->in_lf.ensure(3 * sizeof(float) * nb));
     CUDA_TRY(ctx, ctx->mid.ensure(3 * sizeof(float) * npx));
     CUDA_TRY(ctx, ctx->out_planes.ensure(3 * sizeof(float) * npx));
-    int32_t *dq[3]; float *dlf[3], *mid[3], *dout[3];
+    int32_t *dq[3]; int16_t *dq16[3]; float *dlf[3], *mid[3], *dout[3];
     for (int c = 0; c < 3; c++) {
         dq[c] = ctx->in_q.as<int32_t>() + c * npx;
+        dq16[c] = narrow ? ctx->in_q16.as<int16_t>() + c * npx : nullptr;
         dlf[c] = ctx->in_lf.as<float>() + c * nb;
         mid[c] = ctx->mid.as<float>() + c * npx;
         dout[c] = ctx->out_planes.as<float>() + c * npx;
+    }
+    if (is_subsampled(p)) {
+        // chroma-subsampled frame: plain upload -> stage 1 per channel + upsampling -> stage 2 -> download
+        const int32_t *q3[3]; const float *l3[3];
+        for (int c = 0; c < 3; c++) {
+            const size_t nc = (size_t)(W >> p->shift_x[c]) * (H >> p->shift_y[c]);
+            if (narrow) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(dq16[c], qcoeff[c], sizeof(int16_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
+                widen_i16(ctx, dq16[c], dq[c], nc, ctx->stream);
+            } else {
+                CUDA_TRY(ctx, cudaMemcpyAsync(dq[c], qcoeff[c], sizeof(int32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * (nc / 64), cudaMemcpyHostToDevice, ctx->stream));
+            q3[c] = dq[c]; l3[c] = dlf[c];
+        }
+        HostMaps M;
+        if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
+        if ((rc = invert_subsampled_dev(ctx, p, q3, l3, M.ds, M.hf, mid))) return rc;
+        if ((rc = restore_dev(ctx, p, nullptr, mid, W, M.hf, M.sharp, dout))) return rc;
+        return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
     }
     cudaStream_t comp = ctx->stream, up = ctx->h2d_stream, down = ctx->d2h_stream;
     HostMaps M;
@@ -850,43 +874,45 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], cudaEventDisableTiming));
     }
-    auto slab_y0 = [&](int i) { return slab_start[i]; };
-    auto slab_rows = [&](int i) { return (i + 1 < nslab ? slab_start[i + 1] : H) - slab_start[i]; };
     rc = 0;
-    for (int i = 0; i <= nslab && !rc; i++) {
-        if (i < nslab) {
-            const int y0 = slab_y0(i), rows = slab_rows(i);
-            for (int c = 0; c < 3 && !rc; c++) {
-                cudaError_t e = cudaMemcpyAsync(dq[c] + (size_t)y0 * W, qcoeff[c] + (size_t)y0 * W, sizeof(int32_t) * (size_t)rows * W, cudaMemcpyHostToDevice, up);
-                if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (upload)", e);
-            }
-            if (rc) break;
-            cudaEventRecord(ev_up[i], up);
-            cudaStreamWaitEvent(comp, ev_up[i], 0);
-            // stage 1 of slab i: a frame of `rows` rows whose planes start at row y0
+    for (int i = 0; i < nslab && !rc; i++) {
+        const int y0 = slab_start[i], y1 = i + 1 < nslab ? slab_start[i + 1] : H, rows = y1 - y0;
+        const size_t off = (size_t)y0 * W, cnt = (size_t)rows * W;
+        for (int c = 0; c < 3 && !rc; c++) {
+            cudaError_t e = narrow
+                ? cudaMemcpyAsync(dq16[c] + off, (const int16_t *)qcoeff[c] + off, sizeof(int16_t) * cnt, cudaMemcpyHostToDevice, up)
+                : cudaMemcpyAsync(dq[c] + off, (const int32_t *)qcoeff[c] + off, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, up);
+            if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (upload)", e);
+        }
+        if (rc) break;
+        cudaEventRecord(ev_up[i], up);
+        cudaStreamWaitEvent(comp, ev_up[i], 0);
+        if (narrow)
+            for (int c = 0; c < 3; c++) widen_i16(ctx, dq16[c] + off, dq[c] + off, cnt, comp);
+        {   // stage 1 of slab i: a frame of `rows` rows whose planes start at row y0
             jxlb200_frame_params ps = *p;
             ps.height = rows;
-            const int32_t *q3[3] = {dq[0] + (size_t)y0 * W, dq[1] + (size_t)y0 * W, dq[2] + (size_t)y0 * W};
+            const int32_t *q3[3] = {dq[0] + off, dq[1] + off, dq[2] + off};
             const float *l3[3] = {dlf[0] + (size_t)(y0 / 8) * wb, dlf[1] + (size_t)(y0 / 8) * wb, dlf[2] + (size_t)(y0 / 8) * wb};
-            float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
+            float *m3[3] = {mid[0] + off, mid[1] + off, mid[2] + off};
             rc = invert_dev(ctx, &ps, q3, l3, M.ds + (size_t)(y0 / 8) * wb, M.bo + (size_t)(y0 / 8) * wb, M.hf + (size_t)(y0 / 8) * wb,
                             M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W, false);
             if (rc) break;
         }
-        if (i >= 1) {
-            // stage 2 of slab i-1 (its lower halo rows were written by stage 1 of slab i just above)
-            const int j = i - 1, y0 = slab_y0(j), rows = slab_rows(j);
+        {   // stage 2 of the rows whose lower halo now exists: the slab shifted up by HALO rows
+            const int a = i > 0 ? y0 - JXLB200_HALO_ROWS : 0, b = i + 1 < nslab ? y1 - JXLB200_HALO_ROWS : H, r2 = b - a;
+            const size_t o2 = (size_t)a * W;
             jxlb200_frame_params ps = *p;
-            ps.height = rows;
-            jxlb200_slab sl = {y0, rows, H, j > 0 ? 1 : 0, j < nslab - 1 ? 1 : 0};
-            const float *m3[3] = {mid[0] + (size_t)y0 * W, mid[1] + (size_t)y0 * W, mid[2] + (size_t)y0 * W};
-            float *o3[3] = {dout[0] + (size_t)y0 * W, dout[1] + (size_t)y0 * W, dout[2] + (size_t)y0 * W};
-            rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(y0 / 8) * wb, M.sharp + (size_t)(y0 / 8) * wb, o3);
+            ps.height = r2;
+            jxlb200_slab sl = {a, r2, H, a > 0 ? 1 : 0, b < H ? 1 : 0};
+            const float *m3[3] = {mid[0] + o2, mid[1] + o2, mid[2] + o2};
+            float *o3[3] = {dout[0] + o2, dout[1] + o2, dout[2] + o2};
+            rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(a / 8) * wb, M.sharp + (size_t)(a / 8) * wb, o3);
             if (rc) break;
-            cudaEventRecord(ev_k2[j], comp);
-            cudaStreamWaitEvent(down, ev_k2[j], 0);
+            cudaEventRecord(ev_k2[i], comp);
+            cudaStreamWaitEvent(down, ev_k2[i], 0);
             for (int c = 0; c < 3 && !rc; c++) {
-                cudaError_t e = cudaMemcpyAsync(out[c] + (size_t)y0 * W, o3[c], sizeof(float) * (size_t)rows * W, cudaMemcpyDeviceToHost, down);
+                cudaError_t e = cudaMemcpyAsync(out[c] + o2, o3[c], sizeof(float) * (size_t)r2 * W, cudaMemcpyDeviceToHost, down);
                 if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (download)", e);
             }
         }
@@ -897,6 +923,20 @@ int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params 
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return ctx->fail(JXLB200_E_CUDA, "stream synchronize", e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
     return check_flags(ctx);
+}
+
+int32_t jxlb200_vardct_reconstruct(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    return reconstruct_host(ctx, p, (const void *const *)qcoeff, 4, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, out);
+}
+
+int32_t jxlb200_vardct_reconstruct_i16(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const int16_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    return reconstruct_host(ctx, p, (const void *const *)qcoeff, 2, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, out);
 }
 
 int32_t jxlb200_vardct_invert(jxlb200_ctx *ctx, const jxlb200_frame_params *p,

@@ -135,9 +135,9 @@ class Reconstructor:
         self._weights = (w, off)
 
     # -- VarDCT --
-    def _state_args(self, st, H, W, with_sharp):
+    def _state_args(self, st, H, W, with_sharp, qdtype=np.int32):
         hb, wb, th, tw = H // 8, W // 8, (H + 63) // 64, (W + 63) // 64
-        q = [_c(st["qcoeff"][c], np.int32) for c in range(3)]
+        q = [_c(st["qcoeff"][c], qdtype) for c in range(3)]
         lf = [_c(st["lf"][c], np.float32) for c in range(3)]
         ds, bo = _c(st["dct_select"], np.uint8), _c(st["block_origin"], np.uint8)
         hm = _c(st["hf_mul"], np.int32)
@@ -192,17 +192,32 @@ class Reconstructor:
     def performColorTransforms(self, p, planes_in):
         return self._stage(self._L.jxlb200_color_transform, p, planes_in)
 
-    def reconstruct(self, p, st, out=None):
-        """The whole path on host buffers: invertVarDCT -> Gaborish -> EPF -> colour transform."""
+    def reconstruct(self, p, st, out=None, narrow=False):
+        """The whole path on host buffers: invertVarDCT -> Gaborish -> EPF -> colour transform.
+
+        narrow=True sends the coefficients as int16 (jxlb200_vardct_reconstruct_i16: half the upload, same result);
+        planes that already are int16 go as they are, int32 planes are range-checked and narrowed here."""
         H, W = p.height, p.width
         self._p_for_shapes = p
         try:
-            q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True)
+            if narrow:
+                q16 = []
+                for c in range(3):
+                    a = np.asarray(st["qcoeff"][c])
+                    if a.dtype != np.int16:
+                        if a.size and (int(a.max()) > 32767 or int(a.min()) < -32768):
+                            raise ValueError("qcoeff[%d] does not fit int16: use narrow=False" % c)
+                        a = a.astype(np.int16)
+                    q16.append(np.ascontiguousarray(a))
+                st = dict(st)
+                st["qcoeff"] = q16
+            q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True, np.int16 if narrow else np.int32)
         finally:
             self._p_for_shapes = None
         if out is None:
             out = np.empty((3, H, W), np.float32)
-        self._check(self._L.jxlb200_vardct_reconstruct(
+        fn = self._L.jxlb200_vardct_reconstruct_i16 if narrow else self._L.jxlb200_vardct_reconstruct
+        self._check(fn(
             self._h, C.byref(p), _lib.planes([_ptr(a) for a in q]), _lib.planes([_ptr(a) for a in lf]),
             _ptr(ds), _ptr(bo), _ptr(hm), _ptr(xf), _ptr(bf), _ptr(sh), _lib.planes([_ptr(out[c]) for c in range(3)])))
         return out

@@ -258,3 +258,32 @@ def test_host_entry_slab_schedule_exact(recon, orc, H):
     p = default_frame_params(W, H, epf_iters=3)
     st = _state(W, H, 100 + H, p, mix="small")
     assert np.array_equal(recon.reconstruct(p, st), orc.vardct_reconstruct(p, st, nthreads=8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H", [8, 520, 1288])
+def test_host_entry_int16_coefficients_exact(recon, orc, H):
+    """jxlb200_vardct_reconstruct_i16: coefficients narrowed to int16 by the caller, widened on the device -- the int32
+    call's result bit for bit, on a single slab and on pipelined ones."""
+    W = 72
+    p = default_frame_params(W, H, epf_iters=3)
+    st = _state(W, H, 300 + H, p, mix="small")
+    want = orc.vardct_reconstruct(p, st, nthreads=8)
+    assert np.array_equal(recon.reconstruct(p, st, narrow=True), want)
+    st16 = dict(st)
+    st16["qcoeff"] = [np.ascontiguousarray(st["qcoeff"][c], dtype=np.int16) for c in range(3)]
+    assert np.array_equal(recon.reconstruct(p, st16, narrow=True), want)
+    wide = dict(st)
+    wide["qcoeff"] = [st["qcoeff"][c].copy() for c in range(3)]
+    wide["qcoeff"][1][0, 1] = 40000
+    with pytest.raises(ValueError):
+        recon.reconstruct(p, wide, narrow=True)
+
+
+@pytest.mark.gpu
+def test_chroma_subsampled_frame_int16_coefficients_exact(recon, orc):
+    W, H = 272, 144
+    p, st, qw, qo = _subsampled_state(W, H, (1, 0, 1), (1, 0, 1), seed=0x4A584C00 + 78)
+    p.gab, p.epf_iters = 1, 2
+    recon.setWeights(qw, qo)
+    assert np.array_equal(recon.reconstruct(p, st, narrow=True), orc.vardct_reconstruct(p, st, nthreads=4))

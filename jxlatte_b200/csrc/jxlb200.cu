@@ -59,6 +59,9 @@ struct jxlb200_ctx {
     std::vector<cudaEvent_t> ev_pool;
 
     DevBuf sched, items, gate, wraw, woff, wexp, cosbig, lut8, sigma, flags;
+    float lut8_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // what lut8 holds on the device, and the stream that put it there
+    cudaStream_t lut8_stream = nullptr;
+    bool lut8_valid = false;
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_q16, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
@@ -370,7 +373,15 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
             CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->flags.p, 0, sizeof(int) * 4, st));
         }
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->lut8.p, K.sharp_lut, sizeof(float) * 8, cudaMemcpyHostToDevice, st));
+        // K.sharp_lut lives in pageable memory, and an asynchronous copy from pageable memory first waits for everything
+        // enqueued on its stream: once per slab that stalled the host behind stage 1 and left the upload engine idle meanwhile.
+        // The table rarely changes (RestorationFilter.java:18-44), so it goes up only when it differs from the device's copy.
+        if (!ctx->lut8_valid || ctx->lut8_stream != st || memcmp(ctx->lut8_host, K.sharp_lut, sizeof(float) * 8) != 0) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->lut8.p, K.sharp_lut, sizeof(float) * 8, cudaMemcpyHostToDevice, st));
+            memcpy(ctx->lut8_host, K.sharp_lut, sizeof(float) * 8);
+            ctx->lut8_stream = st;
+            ctx->lut8_valid = true;
+        }
         inv_sigma = ctx->sigma.as<float>() + wb;
         const int br0 = K.has_top ? -1 : 0, br1 = (rows / 8) * n_frames + (K.has_bottom ? 1 : 0);
         k2_sigma<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(hf_mul, sharp, wb, br0, br1, K.gscale,
@@ -763,6 +774,9 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 // Slab schedule of the pipelined host entry point: the first two and the last two slabs are one group row (256) each so
 // that the pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS.
 static void host_slab_schedule(int H, std::vector<int> &slab_start);
+#ifndef JXLB200_HOST_TWO_COMPUTE_STREAMS
+#define JXLB200_HOST_TWO_COMPUTE_STREAMS 1   /* measured on B200, 8K frame, int32 / int16 coefficients: one compute stream 10.40 / 9.29 ms, two 10.31 / 9.21 ms (256-row slabs: 11.07 / 11.49 -> 10.53 / 10.39) */
+#endif
 #ifndef JXLB200_PIPE_ROWS
 #define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
 #endif
@@ -855,7 +869,10 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
         if ((rc = restore_dev(ctx, p, nullptr, mid, W, M.hf, M.sharp, dout))) return rc;
         return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
     }
+    // stage 2 of one slab and stage 1 of the next touch disjoint rows and disjoint context buffers, so they run on two
+    // streams: on slab-sized pieces stage 1 is a chain of short latency-bound launches, which hide under the issue-bound k2
     cudaStream_t comp = ctx->stream, up = ctx->h2d_stream, down = ctx->d2h_stream;
+    cudaStream_t comp2 = JXLB200_HOST_TWO_COMPUTE_STREAMS ? ctx->k1_stream[0] : comp;
     HostMaps M;
     {   // the small per-block maps go first, on the upload stream
         cudaStream_t keep = ctx->stream;
@@ -869,10 +886,11 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
     std::vector<int> slab_start;
     host_slab_schedule(H, slab_start);
     const int nslab = (int)slab_start.size();
-    std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab);
+    std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab), ev_k1(nslab);
     for (int i = 0; i < nslab; i++) {
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k1[i], cudaEventDisableTiming));
     }
     rc = 0;
     for (int i = 0; i < nslab && !rc; i++) {
@@ -907,9 +925,15 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             jxlb200_slab sl = {a, r2, H, a > 0 ? 1 : 0, b < H ? 1 : 0};
             const float *m3[3] = {mid[0] + o2, mid[1] + o2, mid[2] + o2};
             float *o3[3] = {dout[0] + o2, dout[1] + o2, dout[2] + o2};
+            if (comp2 != comp) {
+                cudaEventRecord(ev_k1[i], comp);
+                cudaStreamWaitEvent(comp2, ev_k1[i], 0);
+            }
+            ctx->stream = comp2;
             rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(a / 8) * wb, M.sharp + (size_t)(a / 8) * wb, o3);
+            ctx->stream = comp;
             if (rc) break;
-            cudaEventRecord(ev_k2[i], comp);
+            cudaEventRecord(ev_k2[i], comp2);
             cudaStreamWaitEvent(down, ev_k2[i], 0);
             for (int c = 0; c < 3 && !rc; c++) {
                 cudaError_t e = cudaMemcpyAsync(out[c] + o2, o3[c], sizeof(float) * (size_t)r2 * W, cudaMemcpyDeviceToHost, down);
@@ -918,7 +942,8 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
         }
     }
     cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(down);
-    for (int i = 0; i < nslab; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k2[i]); }
+    if (comp2 != comp && e2 == cudaSuccess) e2 = cudaStreamSynchronize(comp2);
+    for (int i = 0; i < nslab; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k2[i]); cudaEventDestroy(ev_k1[i]); }
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return ctx->fail(JXLB200_E_CUDA, "stream synchronize", e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));

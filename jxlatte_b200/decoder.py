@@ -531,10 +531,20 @@ class JXLDecoder:
                 rgb = self.engine.color(q, xyb)
                 for c in range(3):
                     bufs[c] = _Buf(np.ascontiguousarray(rgb[c, :hh, :ww]))
+            adopt = False
             if canvas is None:
-                dt = bufs[0].a.dtype
-                canvas = [_Buf(np.zeros((info["height"], info["width"]), dt)) for _ in range(colors + nextra)]
-            if f["type"] in (0, 3):
+                # The usual still image: ONE VarDCT frame that covers the image and REPLACEs.  copyToCanvas would copy every
+                # sample of it into a zeroed canvas (page faults included: 2 ms per megapixel and channel); the planes are
+                # freshly made numpy arrays nobody else holds, so they become the canvas.
+                adopt = (f["type"] in (0, 3) and f["encoding"] == ENC_VARDCT and nextra == 0 and colors == frame_colors == len(bufs)
+                         and (fy0, fx0) == (0, 0) and all(b.a.shape == (info["height"], info["width"]) and not b.is_int for b in bufs)
+                         and (f["blend_mode"] == 0 or (f["blend_mode"] == 1 and reference[f["blend_source"]] is None)))
+                if adopt:
+                    canvas = list(bufs)
+                else:
+                    dt = bufs[0].a.dtype
+                    canvas = [_Buf(np.zeros((info["height"], info["width"]), dt)) for _ in range(colors + nextra)]
+            if f["type"] in (0, 3) and not adopt:
                 aliased = any(reference[i] is canvas and i != f["save_as_reference"] for i in range(4))
                 if aliased:
                     canvas = [_Buf(b.a.copy()) for b in canvas]

@@ -793,6 +793,23 @@ static void host_slab_schedule(int H, std::vector<int> &slab_start) {
         g += take;
     }
 }
+// rows [a, b) that stage 2 produces (and the download returns) once stage 1 of slab i has run: the slab shifted up by the halo
+static inline void host_stage2_range(const std::vector<int> &slab_start, int H, int i, int &a, int &b) {
+    const int n = (int)slab_start.size();
+    a = i > 0 ? slab_start[i] - JXLB200_HALO_ROWS : 0;
+    b = i + 1 < n ? slab_start[i + 1] - JXLB200_HALO_ROWS : H;
+}
+int32_t jxlb200_host_stage2_ranges(int32_t height, int32_t *first_rows, int32_t *end_rows, int32_t capacity) {
+    if (height <= 0 || (height & 7)) return JXLB200_E_ARG;
+    std::vector<int> v;
+    host_slab_schedule(height, v);
+    for (int i = 0; i < (int)v.size() && first_rows && end_rows && i < capacity; i++) {
+        int a, b;
+        host_stage2_range(v, height, i, a, b);
+        first_rows[i] = a; end_rows[i] = b;
+    }
+    return (int32_t)v.size();
+}
 // the schedule, for callers that want to overlap their own work with the slabs and for the CPU tests (no device needed)
 int32_t jxlb200_host_slab_schedule(int32_t height, int32_t *starts, int32_t capacity) {
     if (height <= 0 || (height & 7)) return JXLB200_E_ARG;
@@ -918,7 +935,9 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             if (rc) break;
         }
         {   // stage 2 of the rows whose lower halo now exists: the slab shifted up by HALO rows
-            const int a = i > 0 ? y0 - JXLB200_HALO_ROWS : 0, b = i + 1 < nslab ? y1 - JXLB200_HALO_ROWS : H, r2 = b - a;
+            int a, b;
+            host_stage2_range(slab_start, H, i, a, b);
+            const int r2 = b - a;
             const size_t o2 = (size_t)a * W;
             jxlb200_frame_params ps = *p;
             ps.height = r2;

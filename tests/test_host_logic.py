@@ -71,3 +71,26 @@ def test_host_entry_slab_schedule_partitions_the_frame():
     assert L.jxlb200_host_slab_schedule(4320, None, 0) == 11          # count only
     assert L.jxlb200_host_slab_schedule(12, None, 0) == _lib.E_ARG    # heights are padded to 8
     assert L.jxlb200_host_slab_schedule(0, None, 0) == _lib.E_ARG
+
+
+def test_host_entry_stage2_ranges_follow_the_slabs_by_one_halo():
+    """jxlb200_host_stage2_ranges (needs no device): after stage 1 of slab i the host entry point runs stage 2 on the slab
+    shifted up by the 8 halo rows, so a range never reads stage-1 rows of a slab that has not been uploaded yet, and the ranges
+    cover the frame exactly once."""
+    import ctypes as C
+    from jxlatte_b200 import _lib
+    L = _lib.lib()
+    for H in (8, 64, 256, 264, 512, 520, 776, 1032, 2048, 2056, 4320, 16384):
+        starts = (C.c_int32 * 512)()
+        n = L.jxlb200_host_slab_schedule(H, starts, 512)
+        a, b = (C.c_int32 * 512)(), (C.c_int32 * 512)()
+        assert L.jxlb200_host_stage2_ranges(H, a, b, 512) == n
+        s = list(starts[:n]) + [H]
+        assert a[0] == 0 and b[n - 1] == H
+        for i in range(n):
+            assert b[i] - a[i] >= 8 and a[i] % 8 == 0 and b[i] % 8 == 0
+            if i:
+                assert a[i] == b[i - 1] == s[i] - _lib.HALO_ROWS          # contiguous, one halo above the slab's first row
+            # rows the range reads (itself plus HALO_ROWS above and below, clipped to the frame) are stage-1 output of slabs <= i
+            assert min(b[i] + _lib.HALO_ROWS, H) <= s[i + 1]
+    assert L.jxlb200_host_stage2_ranges(12, None, None, 0) == _lib.E_ARG

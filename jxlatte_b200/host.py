@@ -46,6 +46,23 @@ def _ptr(a):
     return a.ctypes.data
 
 
+def narrow_coefficients(qcoeff):
+    """The three coefficient planes as contiguous int16 arrays for jxlb200_vardct_reconstruct_i16.  Planes that already are
+    int16 pass through untouched (no copy: pinned buffers stay pinned); wider ones are range-checked first -- a coefficient
+    beyond int16 is legal JPEG XL, it just has to take the int32 call."""
+    out = []
+    for c in range(3):
+        a = np.asarray(qcoeff[c])
+        if a.dtype != np.int16:
+            if a.dtype.kind not in "iu":
+                raise ValueError("qcoeff[%d] is not an integer array" % c)
+            if a.size and (int(a.max()) > 32767 or int(a.min()) < -32768):
+                raise ValueError("qcoeff[%d] does not fit int16: use narrow=False" % c)
+            a = a.astype(np.int16)
+        out.append(np.ascontiguousarray(a))
+    return out
+
+
 def qm_default_params():
     """HFGlobal.getDefaultParams (J/frame/vardct/HFGlobal.java:79-188)."""
     prm = (QmParams * 17)()
@@ -201,16 +218,8 @@ class Reconstructor:
         self._p_for_shapes = p
         try:
             if narrow:
-                q16 = []
-                for c in range(3):
-                    a = np.asarray(st["qcoeff"][c])
-                    if a.dtype != np.int16:
-                        if a.size and (int(a.max()) > 32767 or int(a.min()) < -32768):
-                            raise ValueError("qcoeff[%d] does not fit int16: use narrow=False" % c)
-                        a = a.astype(np.int16)
-                    q16.append(np.ascontiguousarray(a))
                 st = dict(st)
-                st["qcoeff"] = q16
+                st["qcoeff"] = narrow_coefficients(st["qcoeff"])
             q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True, np.int16 if narrow else np.int32)
         finally:
             self._p_for_shapes = None

@@ -94,3 +94,26 @@ def test_host_entry_stage2_ranges_follow_the_slabs_by_one_halo():
             # rows the range reads (itself plus HALO_ROWS above and below, clipped to the frame) are stage-1 output of slabs <= i
             assert min(b[i] + _lib.HALO_ROWS, H) <= s[i + 1]
     assert L.jxlb200_host_stage2_ranges(12, None, None, 0) == _lib.E_ARG
+
+
+def test_narrow_coefficients_checks_the_range_and_keeps_int16_planes():
+    """host.narrow_coefficients feeds jxlb200_vardct_reconstruct_i16: int16 planes go through without a copy, int32 planes
+    are narrowed only when every coefficient fits."""
+    import numpy as np
+    import pytest
+    from jxlatte_b200.host import narrow_coefficients
+    rng = np.random.default_rng(5)
+    q = [rng.integers(-32768, 32768, size=(16, 24), dtype=np.int32) for _ in range(3)]
+    n = narrow_coefficients(q)
+    assert all(a.dtype == np.int16 and a.flags.c_contiguous and np.array_equal(a, b) for a, b in zip(n, q))
+    again = narrow_coefficients(n)
+    assert all(a is b or np.shares_memory(a, b) for a, b in zip(again, n))
+    stacked = np.stack(n)                                    # one (3, H, W) array works like a list of planes
+    assert all(np.shares_memory(a, stacked) for a in narrow_coefficients(stacked))
+    for bad in (32768, -32769):
+        w = [a.copy() for a in q]
+        w[2][3, 4] = bad
+        with pytest.raises(ValueError):
+            narrow_coefficients(w)
+    with pytest.raises(ValueError):
+        narrow_coefficients([a.astype(np.float32) for a in q])

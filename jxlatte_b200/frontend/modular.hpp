@@ -384,12 +384,14 @@ class ModularStream {
         const bool use_wp = ch.force_wp || tree_->uses_wp;
         if (use_wp) coverage().wp_channels++;
         const int H = ch.h, W = ch.w;
+        // The weighted predictor looks at its errors on the current and the previous row only (W, WW, N, NW, NE), and a pixel's
+        // own prediction is used at that pixel only: two rows per error plane (row y lives at (y & 1) * W) and one scalar, not
+        // the six H x W planes of the Java.  Positions of row y are read only after they were written in row y, so the stale
+        // row y - 2 underneath never shows.
         std::vector<int32_t> err[5];
-        std::vector<int32_t> wp_pred;
-        if (use_wp) {
-            for (auto &e : err) e.assign((size_t)H * W, 0);
-            wp_pred.assign((size_t)H * W, 0);
-        }
+        int32_t wp_pred = 0;
+        if (use_wp)
+            for (auto &e : err) e.assign((size_t)2 * W, 0);
         const std::vector<MATree::Node> &nodes = tree_->nodes;
         // properties 0 (channel) and 1 (stream) are constant here: skip straight through those nodes
         int root = 0;
@@ -411,24 +413,25 @@ class ModularStream {
                 const MATree::Node &leaf = nodes[at];
                 const uint32_t sym = symbols_.read(br, leaf.context, dist_multiplier_);
                 const int32_t diff = detail::wrap_add(detail::wrap_mul(unpack_signed(sym), leaf.multiplier), leaf.offset);
-                const int32_t value = detail::wrap_add(diff, detail::predict(ch, y, x, leaf.predictor, use_wp ? wp_pred[(size_t)y * W + x] : 0));
+                const int32_t value = detail::wrap_add(diff, detail::predict(ch, y, x, leaf.predictor, use_wp ? wp_pred : 0));
                 ch.at(y, x) = value;
                 if (use_wp) {
                     const int32_t v3 = detail::wrap_shl(value, 3);
+                    const size_t at_e = (size_t)(y & 1) * W + x;
                     for (int e = 0; e < 4; e++)
-                        err[e][(size_t)y * W + x] = detail::wrap_add(detail::iabs(detail::wrap_sub(sub[e], v3)), 3) >> 3;
-                    err[4][(size_t)y * W + x] = detail::wrap_sub(wp_pred[(size_t)y * W + x], v3);
+                        err[e][at_e] = detail::wrap_add(detail::iabs(detail::wrap_sub(sub[e], v3)), 3) >> 3;
+                    err[4][at_e] = detail::wrap_sub(wp_pred, v3);
                 }
             }
         }
     }
 
     // ModularChannel.prePredictWP :185-236
-    int32_t wp_prepare(const Channel &ch, const std::vector<int32_t> (&err)[5], std::vector<int32_t> &pred, int32_t (&sub)[4], int x, int y) const {
+    int32_t wp_prepare(const Channel &ch, const std::vector<int32_t> (&err)[5], int32_t &pred, int32_t (&sub)[4], int x, int y) const {
         using namespace detail;
         const int W = ch.w;
         const Nb n{ch};
-        auto E = [&](int e, int yy, int xx) { return err[e][(size_t)yy * W + xx]; };
+        auto E = [&](int e, int yy, int xx) { return err[e][(size_t)(yy & 1) * W + xx]; };     // two-row ring, see decode_channel
         auto eW = [&](int e) { return x > 0 ? E(e, y, x - 1) : 0; };
         auto eN = [&](int e) { return y > 0 ? E(e, y - 1, x) : 0; };
         auto eWW = [&](int e) { return x > 1 ? E(e, y, x - 2) : 0; };
@@ -469,7 +472,7 @@ class ModularStream {
         for (int e = 0; e < 4; e++) s += wrap_mul(sub[e], weight[e]);
         int32_t p = (int32_t)((s * ((1 << 24) / wsum)) >> 24);
         if (((tN ^ tW) | (tN ^ tNW)) <= 0) p = clamp3(p, w3, n3, ne3);
-        pred[(size_t)y * W + x] = p;
+        pred = p;
         int32_t m = tW;
         if (iabs(tN) > iabs(m)) m = tN;
         if (iabs(tNW) > iabs(m)) m = tNW;

@@ -161,8 +161,10 @@ inline int extract_codestream(const std::vector<uint8_t> &file, std::vector<uint
             size = be(at + 8, 8);
             header = 16;
         }
-        size_t payload_end = size == 0 ? file.size() : at + (size_t)size;
-        if (size != 0 && (size < header || payload_end > file.size())) throw StreamError("illegal box size");
+        // compare against the bytes that are left, never form at + size first: a 64-bit extended size near 2^64 would wrap
+        if (size != 0 && (size < header || size > (uint64_t)(file.size() - at))) throw StreamError("illegal box size");
+        const size_t payload_end = size == 0 ? file.size() : at + (size_t)size;
+        if (payload_end <= at) throw StreamError("illegal box size");       // the walk always moves forward
         size_t body = at + header;
         if (tag == 0x6a786c6c) {                 // jxll
             if (payload_end - body != 1) throw StreamError("jxll box must hold one byte");

@@ -26,6 +26,8 @@ struct Coverage {
                      &rct, &raw_quant, &custom_quant, &lf_smoothing}) *p = 0;
     }
 };
+// Diagnostic counters only: process-wide and reset by every jxlf_decode, so two decodes running at once (ctypes releases the
+// GIL) report each other's counts; no parsed state depends on them and every field is atomic.
 inline Coverage &coverage() { static Coverage c; return c; }
 
 struct HybridConfig {

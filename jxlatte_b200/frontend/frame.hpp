@@ -5,6 +5,7 @@
 // group/PassGroup.java:67-84, vardct/LFCoefficients.java, HFMetadata.java, HFBlockContext.java, HFGlobal.java:194-302,
 // HFPass.java, HFCoefficients.java:49-138,230-265.
 #pragma once
+#include <array>
 #include <cmath>
 #include <map>
 
@@ -210,6 +211,11 @@ class FrameDecoder {
             for (auto &e : ih_.extra) alpha_channels += e.type == 0;
             EntropyStream es(br, 10);
             f.num_patches = (int)es.read(br, 0);
+            // a one-symbol ANS distribution costs no bits per symbol, so the counts are untrusted: bound patches and positions by
+            // the frame's pixel count (a patch position names at least one pixel), capped like the spline control points
+            const uint64_t patch_cap = std::min<uint64_t>((uint64_t)std::max(h.width, 1) * (uint64_t)std::max(h.height, 1), 1u << 20);
+            if (f.num_patches < 0 || (uint64_t)f.num_patches > patch_cap) throw StreamError("too many patches");
+            uint64_t total_positions = 0;
             f.patches.resize(f.num_patches);
             for (PatchInfo &pt : f.patches) {
                 pt.ref = (int)es.read(br, 1);
@@ -219,6 +225,8 @@ class FrameDecoder {
                 pt.h = 1 + (int)es.read(br, 2);
                 const uint32_t count = 1 + es.read(br, 7);
                 if ((int32_t)count <= 0) throw StreamError("patch count overflow");
+                total_positions += count;
+                if (total_positions > patch_cap) throw StreamError("too many patch positions");
                 int32_t px = 0, py = 0;
                 for (uint32_t j = 0; j < count; j++) {
                     if (j == 0) {
@@ -371,6 +379,7 @@ class FrameDecoder {
             Channel c = f.modular.channels[idx];
             c.px.clear();
             c.decoded = false;
+            if (c.vshift < 0 || c.vshift > 30 || c.hshift < 0 || c.hshift > 30) throw StreamError("modular channel shift out of range");
             const int gh = dim >> c.vshift, gw = dim >> c.hshift;
             if (gh <= 0 || gw <= 0) throw StreamError("modular channel shift exceeds the group size");
             const int stride = ceil_div(c.w, gw);
@@ -691,9 +700,17 @@ class FrameDecoder {
 
     // ---- passes (Pass.java, HFPass.java) ----
     static const std::vector<uint32_t> &natural_order(int order_id) {
-        static std::vector<uint32_t> cache[13];
-        std::vector<uint32_t> &o = cache[order_id];
-        if (!o.empty()) return o;
+        // all 13 tables are built once, under the function-static's initialisation lock: two threads parsing at once
+        // (ctypes releases the GIL) can never see a half-filled table
+        static const std::array<std::vector<uint32_t>, 13> cache = [] {
+            std::array<std::vector<uint32_t>, 13> t;
+            for (int b = 0; b < 13; b++) t[b] = build_natural_order(b);
+            return t;
+        }();
+        return cache[order_id];
+    }
+    static std::vector<uint32_t> build_natural_order(int order_id) {
+        std::vector<uint32_t> o;
         const int H = kOrderShape[order_id][0], W = kOrderShape[order_id][1], bh = H >> 3, bw = W >> 3, md = std::max(bh, bw);
         struct Key { int llf, k1, k2; uint32_t pos; };
         std::vector<Key> keys;

@@ -15,6 +15,7 @@
 #include "k2_restore.cuh"
 #include "k2_fused.cuh"
 #include "k2_exact.cuh"
+#include "k2_stream.cuh"
 #include "k2_pair.cuh"
 #include "k3_modular.cuh"
 #include "k6_subsample.cuh"
@@ -146,6 +147,7 @@ int upload_constants(jxlb200_ctx *ctx) {
     CUDA_TRY(ctx, (big_attr<128, 1>())); CUDA_TRY(ctx, (big_attr<256, 1>()));
     CUDA_TRY(ctx, k2_fused_init_all());
     CUDA_TRY(ctx, k2_exact_init_all());
+    CUDA_TRY(ctx, k2_stream_init_all());
     CUDA_TRY(ctx, k2_pair_init_all());
     return 0;
 }
@@ -388,8 +390,14 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                      ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3) && k2_exact_supported(K)) {   // default: fused, bit-exact
-        if (ctx->opt_stage2 == 0) k2_exact_dispatch(K, inv_sigma, st, n_frames);     // one 2x2 block per thread
+    if (ctx->opt_stage2 == 0 && k2_stream_supported(K, n_frames) && k2_stream_launch(K, inv_sigma, st, n_frames, ctx->sms) == 0) {
+        // default: the persistent warp-specialised stream (TMA-fed rings, one role per warp), bit-exact
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 0;
+    }
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 4) && k2_exact_supported(K)) {   // fused tile kernels, bit-exact
+        if (ctx->opt_stage2 != 3) k2_exact_dispatch(K, inv_sigma, st, n_frames);     // one 2x2 block per thread (round 1's default; planes the TMA path cannot take)
         else k2_pair_dispatch(K, inv_sigma, st, n_frames);    // two blocks per thread on packed FP32x2: same bits, measured slower
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
@@ -581,7 +589,7 @@ int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return JXLB200_E_ARG;
-    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 3) { ctx->opt_stage2 = value; return 0; }
+    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 4) { ctx->opt_stage2 = value; return 0; }
     if (option == JXLB200_OPT_OVERLAP_ROWS && value >= 0 && (value & 255) == 0) { ctx->opt_overlap_rows = value; return 0; }
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
@@ -729,7 +737,7 @@ int32_t jxlb200_vardct_reconstruct_batch_dev(jxlb200_ctx *ctx, const jxlb200_fra
     if (rc) return rc;
     K2Params K;
     fill_k2(K, p, nullptr);
-    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3) && k2_exact_supported(K)) {   // one launch, blockIdx.z = frame
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 4) && k2_exact_supported(K)) {   // one launch over the whole stack
         const float *m3[3] = {mid[0], mid[1], mid[2]};
         return restore_dev(ctx, p, nullptr, m3, W, hf_mul, sharpness, out, n_frames);
     }

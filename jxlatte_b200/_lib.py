@@ -16,7 +16,7 @@ QM_FLOATS = 3 * 131584
 HALO_ROWS = 8
 OPT_STAGE2 = 1
 OPT_OVERLAP_ROWS = 2
-STAGE2_AUTO, STAGE2_STAGED, STAGE2_FUSED, STAGE2_PAIR, STAGE2_TILE = 0, 1, 2, 3, 4
+STAGE2_AUTO, STAGE2_STAGED, STAGE2_FUSED, STAGE2_PAIR, STAGE2_STREAM = 0, 1, 2, 3, 5
 
 
 class QmParams(C.Structure):

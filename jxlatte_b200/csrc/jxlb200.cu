@@ -71,6 +71,7 @@ struct jxlb200_ctx {
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_q16, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    DevBuf packed;          // interleaved 8/16-bit samples of jxlb200_vardct_reconstruct_packed
     DevBuf blend;           // five compact rectangles of jxlb200_blend
     DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
     DevTables tab;
@@ -572,7 +573,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend, &ctx->packed};
     for (DevBuf *b : all) b->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -871,15 +872,35 @@ static void widen_i16(jxlb200_ctx *ctx, const int16_t *in, int32_t *out, size_t 
 }
 
 // qbytes = 4: qcoeff planes are int32 (HFCoefficients.quantizedCoeffs as the reference holds them); 2: int16
+// Packed output (jxlb200_vardct_reconstruct_packed): the colour planes leave the device as interleaved 8- or 16-bit samples
+struct PackedOut {
+    uint8_t *dst = nullptr;     // crop_h x crop_w x 3 samples
+    int bits = 0, linear = 0, crop_w = 0, crop_h = 0;
+};
+
 static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const void *const qcoeff[3], int qbytes,
     const float *const lf[3], const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
-    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3], const PackedOut *pk = nullptr) {
     int rc = check_params(ctx, p);
     if (rc) return rc;
-    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !sharpness || !out)
+    if (!qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !sharpness || (!out && !pk))
         return ctx->fail(JXLB200_E_ARG, "NULL pointer");
     for (int c = 0; c < 3; c++)
-        if (!qcoeff[c] || !lf[c] || !out[c]) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+        if (!qcoeff[c] || !lf[c] || (!pk && !out[c])) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+    const size_t pk_row = pk ? (size_t)pk->crop_w * 3 * (pk->bits > 8 ? 2 : 1) : 0;
+    if (pk) CUDA_TRY(ctx, ctx->packed.ensure(pk_row * pk->crop_h + 64));
+    // rows [a, b) of the device planes -> packed samples -> host, on stream st (enqueued after stage 2 of those rows)
+    auto send_packed = [&](float *const dplanes[3], int a, int b, cudaStream_t kst, cudaStream_t cst, cudaEvent_t ev) -> int {
+        b = b < pk->crop_h ? b : pk->crop_h;
+        if (a >= b) return 0;
+        const long long quads = (long long)(b - a) * ((pk->crop_w + 3) >> 2);
+        const int grid = (int)(quads / 256 + 1 < (long long)ctx->sms * 8 ? quads / 256 + 1 : (long long)ctx->sms * 8);
+        k8_pack_rgb<<<grid, 256, 0, kst>>>(dplanes[0], dplanes[1], dplanes[2], p->width, a, b, pk->crop_w, pk->linear, pk->bits, ctx->packed.as<unsigned char>());
+        ctx->launches++;
+        if (kst != cst) { cudaEventRecord(ev, kst); cudaStreamWaitEvent(cst, ev, 0); }
+        cudaError_t e = cudaMemcpyAsync(pk->dst + pk_row * a, ctx->packed.as<unsigned char>() + pk_row * a, pk_row * (b - a), cudaMemcpyDeviceToHost, cst);
+        return e == cudaSuccess ? 0 : ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (packed download)", e);
+    };
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int W = p->width, H = p->height, wb = W >> 3, tw = (W + 63) >> 6;
     const size_t npx = (size_t)W * H, nb = npx / 64;
@@ -915,6 +936,11 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
         if ((rc = upload_maps(ctx, p, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, M))) return rc;
         if ((rc = invert_subsampled_dev(ctx, p, q3, l3, M.ds, M.hf, mid))) return rc;
         if ((rc = restore_dev(ctx, p, nullptr, mid, W, M.hf, M.sharp, dout))) return rc;
+        if (pk) {
+            if ((rc = send_packed(dout, 0, H, ctx->stream, ctx->stream, nullptr))) return rc;
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            return check_flags(ctx);
+        }
         return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
     }
     // stage 2 of one slab and stage 1 of the next touch disjoint rows and disjoint context buffers, so they run on two
@@ -983,6 +1009,11 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(a / 8) * wb, M.sharp + (size_t)(a / 8) * wb, o3);
             ctx->stream = comp;
             if (rc) break;
+            if (pk) {       // sRGB + quantise + interleave on the compute stream, then a quarter (or half) of the bytes go back
+                rc = send_packed(dout, a, b, comp2, down, ev_k2[i]);
+                if (rc) break;
+                continue;
+            }
             cudaEventRecord(ev_k2[i], comp2);
             cudaStreamWaitEvent(down, ev_k2[i], 0);
             for (int c = 0; c < 3 && !rc; c++) {
@@ -1012,6 +1043,21 @@ int32_t jxlb200_vardct_reconstruct_i16(jxlb200_ctx *ctx, const jxlb200_frame_par
     const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
     const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
     return reconstruct_host(ctx, p, (const void *const *)qcoeff, 2, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, out);
+}
+
+int32_t jxlb200_vardct_reconstruct_packed(jxlb200_ctx *ctx, const jxlb200_frame_params *p,
+    const void *const qcoeff[3], int32_t coeff_bytes, const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness,
+    int32_t bits, int32_t linear, int32_t crop_width, int32_t crop_height, uint8_t *out) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (coeff_bytes != 2 && coeff_bytes != 4) return ctx->fail(JXLB200_E_ARG, "coeff_bytes must be 4 (int32) or 2 (int16)");
+    if (bits != 8 && bits != 16) return ctx->fail(JXLB200_E_ARG, "PNG only supports 8 and 16 (PNGWriter.java:57-58)");
+    if (!p || !out || crop_width < 1 || crop_height < 1 || crop_width > p->width || crop_height > p->height)
+        return ctx->fail(JXLB200_E_ARG, "crop size must lie inside the padded frame");
+    PackedOut pk;
+    pk.dst = out; pk.bits = bits; pk.linear = linear ? 1 : 0; pk.crop_w = crop_width; pk.crop_h = crop_height;
+    return reconstruct_host(ctx, p, qcoeff, coeff_bytes, lf, dct_select, block_origin, hf_mul, x_from_y, b_from_y, sharpness, nullptr, &pk);
 }
 
 int32_t jxlb200_vardct_invert(jxlb200_ctx *ctx, const jxlb200_frame_params *p,

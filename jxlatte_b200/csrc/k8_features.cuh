@@ -242,3 +242,43 @@ __global__ void k8_pack_samples(PackArgs A) {
         }
     }
 }
+
+// ---- the same conversion for the three colour planes of a VarDCT frame, rows [r0, r1) x columns [0, cw) of planes with
+// pitch `pitch`, straight after stage 2 on the device: what the pipelined host entry point sends back instead of 12 bytes of
+// float per pixel (jxlb200_vardct_reconstruct_packed).  Four pixels per thread: three 128-bit loads, 12 or 24 bytes out.
+__device__ __forceinline__ int pack_one(float v, int linear, int maxv) {
+    if (linear) {       // TF_SRGB.fromLinearF, J/color/TransferFunction.java:39-43
+        if (v < 0.00313066844250063f) v = __fmul_rn(v, 12.92f);
+        else v = __fadd_rn(__fmul_rn(1.055f, (float)pow((double)v, 0.4166666666666667)), -0.055f);
+    }
+    int q = java_f2i(__fadd_rn(__fmul_rn(v, (float)maxv), 0.5f));      // ImageBuffer.castToIntWithMax, J/util/ImageBuffer.java:129-145
+    return q < 0 ? 0 : (q > maxv ? maxv : q);
+}
+__global__ void k8_pack_rgb(const float *__restrict__ p0, const float *__restrict__ p1, const float *__restrict__ p2, long long pitch,
+                            int r0, int r1, int cw, int linear, int bits, unsigned char *__restrict__ out) {
+    const int quads = (cw + 3) >> 2;
+    const long long n = (long long)(r1 - r0) * quads;
+    const int maxv = (1 << bits) - 1, bytes = bits > 8 ? 2 : 1;
+    const bool vec = (pitch & 3) == 0 && ((((size_t)p0 | (size_t)p1 | (size_t)p2) & 15) == 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = r0 + (int)(i / quads), x = 4 * (int)(i % quads);
+        const long long o = (long long)r * pitch + x;
+        float a[4], b[4], c[4];
+        const int nv = min(4, cw - x);
+        if (vec && x + 4 <= pitch) {
+            const float4 va = *reinterpret_cast<const float4 *>(p0 + o), vb = *reinterpret_cast<const float4 *>(p1 + o), vc = *reinterpret_cast<const float4 *>(p2 + o);
+            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w; b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
+            c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
+        } else {
+            for (int k = 0; k < 4; k++) { const bool in = k < nv; a[k] = in ? p0[o + k] : 0.0f; b[k] = in ? p1[o + k] : 0.0f; c[k] = in ? p2[o + k] : 0.0f; }
+        }
+        unsigned char *dst = out + ((long long)r * cw + x) * 3 * bytes;
+        for (int k = 0; k < nv; k++) {
+            const int q[3] = {pack_one(a[k], linear, maxv), pack_one(b[k], linear, maxv), pack_one(c[k], linear, maxv)};
+            for (int ch = 0; ch < 3; ch++) {
+                if (bytes == 2) { dst[(3 * k + ch) * 2] = (unsigned char)(q[ch] >> 8); dst[(3 * k + ch) * 2 + 1] = (unsigned char)(q[ch] & 255); }   // PNG is big endian
+                else dst[3 * k + ch] = (unsigned char)q[ch];
+            }
+        }
+    }
+}

@@ -231,6 +231,28 @@ class Reconstructor:
             _ptr(ds), _ptr(bo), _ptr(hm), _ptr(xf), _ptr(bf), _ptr(sh), _lib.planes([_ptr(out[c]) for c in range(3)])))
         return out
 
+    def reconstruct_packed(self, p, st, bits=8, linear=True, crop=None, out=None, narrow=False):
+        """The whole path ending in PNG-ready samples (jxlb200_vardct_reconstruct_packed): sRGB transfer (when `linear`),
+        8/16-bit quantisation and R,G,B interleave on the device; returns uint8 [crop_h, crop_w, 3 * bits/8] (16-bit samples big
+        endian, as PNGWriter writes them).  crop = (width, height) of the image inside the padded frame."""
+        H, W = p.height, p.width
+        cw, ch = crop if crop is not None else (W, H)
+        self._p_for_shapes = p
+        try:
+            if narrow:
+                st = dict(st)
+                st["qcoeff"] = narrow_coefficients(st["qcoeff"])
+            q, lf, ds, bo, hm, xf, bf, sh = self._state_args(st, H, W, True, np.int16 if narrow else np.int32)
+        finally:
+            self._p_for_shapes = None
+        nb = 3 * (2 if bits > 8 else 1)
+        if out is None:
+            out = np.empty((ch, cw, nb), np.uint8)
+        self._check(self._L.jxlb200_vardct_reconstruct_packed(
+            self._h, C.byref(p), _lib.planes([_ptr(a) for a in q]), 2 if narrow else 4, _lib.planes([_ptr(a) for a in lf]),
+            _ptr(ds), _ptr(bo), _ptr(hm), _ptr(xf), _ptr(bf), _ptr(sh), int(bits), 1 if linear else 0, int(cw), int(ch), _ptr(out)))
+        return out
+
     # -- device-pointer calls (bench, multi-GPU): integers are CUdeviceptr values --
     def reconstruct_dev(self, p, q, lf, ds, bo, hm, xf, bf, sh, out):
         self._check(self._L.jxlb200_vardct_reconstruct_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf, sh,

@@ -291,3 +291,24 @@ def test_chroma_subsampled_frame_int16_coefficients_exact(recon, orc):
     p.gab, p.epf_iters = 1, 2
     recon.setWeights(qw, qo)
     assert np.array_equal(recon.reconstruct(p, st, narrow=True), orc.vardct_reconstruct(p, st, nthreads=4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(W=520, H=264, bits=8, narrow=False, crop=(517, 259)), dict(W=328, H=1288, bits=16, narrow=True, crop=(328, 1288)),
+                                 dict(W=72, H=776, bits=8, narrow=True, crop=(65, 770))])
+def test_packed_output_matches_oracle_pack(recon, orc, cfg):
+    """jxlb200_vardct_reconstruct_packed: sRGB transfer + 8/16-bit quantise + interleave on the device (single slab and the
+    pipelined schedule) == the oracle's planes through the oracle's PNGWriter sample pipeline, byte for byte."""
+    W, H = cfg["W"], cfg["H"]
+    p = default_frame_params(W, H, epf_iters=3)
+    st = _state(W, H, 500 + W, p, mix="small") if W < 100 else _state(W, H, 500 + W, p)
+    planes = orc.vardct_reconstruct(p, st, nthreads=8)
+    cw, ch = cfg["crop"]
+    want = orc.pack_samples([np.ascontiguousarray(planes[c][:ch, :cw]) for c in range(3)], [cfg["bits"]] * 3, 3, True, cfg["bits"])
+    got = recon.reconstruct_packed(p, st, bits=cfg["bits"], linear=True, crop=(cw, ch), narrow=cfg["narrow"])
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # without the transfer function (an image that is already display-referred, e.g. JPEG-recompressed YCbCr)
+    want2 = orc.pack_samples([np.ascontiguousarray(planes[c][:ch, :cw]) for c in range(3)], [cfg["bits"]] * 3, 3, False, cfg["bits"])
+    assert np.array_equal(recon.reconstruct_packed(p, st, bits=cfg["bits"], linear=False, crop=(cw, ch)), want2)
+    with pytest.raises(ValueError):
+        recon.reconstruct_packed(p, st, bits=12)

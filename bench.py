@@ -70,11 +70,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_inputs(W, H, seed, epf_iters):
+def make_inputs(W, H, seed, epf_iters, oracle_tables=False):
     from jxlatte_b200 import synth, default_frame_params
-    from jxlatte_b200.host import qm_generate
     p = default_frame_params(W, H, epf_iters=epf_iters, gab=True)
-    qw, qo = qm_generate()
+    if oracle_tables:       # the reference arm must not touch the product library: tables from the CPU restatement
+        from oracle import oracle
+        qw, qo = oracle.qm_default_weights()
+    else:
+        from jxlatte_b200.host import qm_generate
+        qw, qo = qm_generate()
     st = synth.make_state(W, H, seed=seed, params=p, qm_weights=qw, qm_offsets=qo)
     return p, st, qw, qo
 
@@ -83,7 +87,7 @@ def cpu_baseline(nthreads, sample=(2048, 2048), epf_iters=3, reps=1):
     """The CPU restatement of jxlatte's algorithm (oracle 'port'; not the JVM) on a bounded sample of the workload."""
     from oracle import oracle
     W, H = sample
-    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 77, epf_iters)
+    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 77, epf_iters, oracle_tables=True)
     t0 = time.perf_counter()
     for _ in range(reps):
         oracle.vardct_reconstruct(p, st, nthreads=nthreads)
@@ -93,27 +97,37 @@ def cpu_baseline(nthreads, sample=(2048, 2048), epf_iters=3, reps=1):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  jxlatte is pure Java and no JVM exists in
-    this image, so this arm times the C restatement (oracle/, kind 'port') on all host cores, each step a bounded sample."""
+    this image, so this arm times the C restatement (oracle/, kind 'port') on all host cores, each step a bounded sample of
+    the workload; jxlatte itself runs this path on ONE thread, so the single-thread figure is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle
     cores = os.cpu_count() or 1
     iters = 3 if args.workload != "batch2048" else 1
-    W, H = 1024, 1024
-    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 78, iters)
+    W, H = 2048, 2048       # 64 groups: enough parallel work for every host core in both stages
+    p, st, _, _ = make_inputs(W, H, 0x4A584C00 + 78, iters, oracle_tables=True)
     for _ in range(min(args.warmup, 2)):
         oracle.vardct_reconstruct(p, st, nthreads=cores)
+    steps = max(1, args.steps)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         oracle.vardct_reconstruct(p, st, nthreads=cores)
     dt = time.perf_counter() - t0
-    v = W * H * args.steps / 1e6 / dt
-    sample = "%dx%d sample of the workload per step, same varblock mix / gab / EPF %d iters" % (W, H, iters)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    v = W * H * steps / 1e6 / dt
+    t0 = time.perf_counter()
+    p1, st1, _, _ = make_inputs(1024, 1024, 0x4A584C00 + 79, iters, oracle_tables=True)
+    t0 = time.perf_counter()
+    oracle.vardct_reconstruct(p1, st1, nthreads=1)
+    v1 = 1024 * 1024 / 1e6 / (time.perf_counter() - t0)
+    sample = "one %dx%d frame of the workload per step (same varblock mix / gab / EPF %d iterations), not the full %s" % (
+        W, H, iters, "7680x4320 frame" if args.workload == "8k" else "workload")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, iters),
-            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample,
+                             "single_thread": {"value": v1, "unit": "MP/s", "cores": 1,
+                                               "sample": "one 1024x1024 frame; jxlatte runs this path on one thread"}},
             "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -126,10 +140,89 @@ def workload_config(args, iters):
             "l2": "inputs per step exceed the 126 MB L2 (no flush needed)"}
 
 
+class Workload:
+    """One workload's device-resident inputs and its step (one pass of the hot path over one batch)."""
+
+    def __init__(self, name, rec, dev, rank, world):
+        import torch
+        from jxlatte_b200.multigpu import slab_rows, SplitFrame
+        self.name, self.rec, self.world = name, rec, world
+        self.iters = 1 if name == "batch2048" else 3
+        if name == "8k":
+            W, H, nframes = 7680, 4320, 1
+        elif name == "batch2048":
+            W, H, nframes = 2048, 2048, BATCH_FRAMES
+        else:
+            W, H, nframes = 16384, 16384, 1
+        self.W, self.H, self.nframes = W, H, nframes
+        rows = H
+        if name == "split16k":      # contiguous group rows per rank; the rank's seed differs, the frame is "one frame" by shape
+            y0, rows = slab_rows(H, world, rank)
+        self.p, self.st, self.qw, self.qo = make_inputs(W, rows, 0x4A584C00 + 2 + rank, self.iters)
+        rec.setWeights(self.qw, self.qo)
+        keys = ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")
+
+        def dev_t(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        first = {k: dev_t(self.st[k]) for k in keys}
+        first["out"] = torch.empty((3, rows, W), dtype=torch.float32, device=dev)
+        self.first, self.stack, self.halo = first, None, None
+        if nframes > 1:
+            parts = [first]
+            for f in range(1, nframes):
+                _, stf, _, _ = make_inputs(W, H, 0x4A584C00 + 100 * f + rank, self.iters)
+                parts.append({k: dev_t(stf[k]) for k in keys})
+            self.stack = {k: torch.cat([d[k] for d in parts], dim=-2).contiguous() for k in keys}
+            self.stack["out"] = torch.empty((3, H * nframes, W), dtype=torch.float32, device=dev)
+            del parts
+        if name == "split16k":
+            self.halo = SplitFrame(rec, self.p, first, y0, rows, H, rank, world, dev)
+        self.px_per_step_all = W * H if name == "split16k" else W * H * nframes * world
+
+    def step(self):
+        rec, p = self.rec, self.p
+        if self.halo is not None:
+            self.halo.step()
+            return
+        d = self.stack if self.stack is not None else self.first
+        q, lf = [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)]
+        out = [d["out"][c].data_ptr() for c in range(3)]
+        args = (d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(), d["x_from_y"].data_ptr(),
+                d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(), out)
+        if self.stack is not None:
+            rec.reconstruct_batch_dev(p, self.nframes, q, lf, *args)
+        else:
+            rec.reconstruct_dev(p, q, lf, *args)
+
+
+def timed_steps(wl, stream, steps, warmup, barrier, dev, world):
+    """W warm-up steps, then exactly K steps between two events on the launching stream, barrier + synchronize on both sides;
+    returns (max-over-ranks ms for the K steps, launches)."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(max(warmup, 3)):
+        wl.step()
+    wl.rec.sync()
+    barrier()
+    l0 = wl.rec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        wl.step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), wl.rec.launch_count() - l0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from jxlatte_b200.host import Reconstructor, Slab
+    from jxlatte_b200 import _lib
+    from jxlatte_b200.host import Reconstructor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -140,17 +233,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    iters = 1 if args.workload == "batch2048" else 3
-    if args.workload == "8k":
-        W, H, nframes = 7680, 4320, 1
-    elif args.workload == "batch2048":
-        W, H, nframes = 2048, 2048, BATCH_FRAMES
-    else:
-        W, H, nframes = 16384, 16384, 1
-
     rec = Reconstructor(local)
     if os.environ.get("JXLB200_STAGE2"):      # kernel-variant experiments (include/jxlb200.h: JXLB200_OPT_STAGE2); default 0
-        from jxlatte_b200 import _lib
         rec.set_option(_lib.OPT_STAGE2, int(os.environ["JXLB200_STAGE2"]))
     # a real (non-legacy) stream shared by torch's events and the library's kernels: a NULL handle would mean
     # "the context's own stream" to jxlb200_set_stream and the events would time nothing
@@ -158,104 +242,38 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     rec.set_stream(stream.cuda_stream)
 
-    slab = None
-    if args.workload == "split16k":
-        # contiguous group rows per rank; every rank builds the same frame (same seed) and keeps its own rows
-        from jxlatte_b200.multigpu import slab_rows
-        y0, rows = slab_rows(H, world, rank)
-        full_h = H
-    p, st, qw, qo = make_inputs(W, H if args.workload != "split16k" else rows, 0x4A584C00 + 2 + rank, iters)
-    rec.setWeights(qw, qo)
-
-    def dev_t(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-
-    frames = []
-    for f in range(nframes):
-        if f > 0:
-            _, stf, _, _ = make_inputs(W, H, 0x4A584C00 + 100 * f + rank, iters)
-        else:
-            stf = st
-        d = {k: dev_t(stf[k]) for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
-        d["out"] = torch.empty((3, stf["height"], W), dtype=torch.float32, device=dev)
-        frames.append(d)
-
-    stack = None
-    if nframes > 1:
-        # the batch entry point takes the frames stacked vertically in every array
-        stack = {k: torch.cat([d[k] for d in frames], dim=-2).contiguous() for k in
-                 ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
-        stack["out"] = torch.empty((3, H * nframes, W), dtype=torch.float32, device=dev)
-        for d in frames[1:]:
-            d.clear()
-        frames[0]["out"] = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-
-    halo = None
-    if args.workload == "split16k":
-        from jxlatte_b200.multigpu import SplitFrame
-        halo = SplitFrame(rec, p, frames[0], y0, rows, full_h, rank, world, dev)
-
-    def step():
-        if halo is not None:
-            halo.step()
-            return
-        if stack is not None:
-            d = stack
-            rec.reconstruct_batch_dev(p, nframes, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
-                                      d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
-                                      d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
-                                      [d["out"][c].data_ptr() for c in range(3)])
-            return
-        for d in frames:
-            rec.reconstruct_dev(p, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
-                                d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
-                                d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
-                                [d["out"][c].data_ptr() for c in range(3)])
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    wl = Workload(args.workload, rec, dev, rank, world)
+    W, H, iters, p, st = wl.W, wl.H, wl.iters, wl.p, wl.st
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
-        step()
+        wl.step()
     rec.sync()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = rec.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = rec.launch_count() - l0
+    ms_max, launches = timed_steps(wl, stream, args.steps, 0, barrier, dev, world)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)
-    rec.sync()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    px_per_step_all = (W * H * nframes * world) if args.workload != "split16k" else W * H
-    value = px_per_step_all * args.steps / 1e6 / (ms_max / 1e3)
+    value = wl.px_per_step_all * args.steps / 1e6 / (ms_max / 1e3)
 
     # ---- stage timing for the roofline of the dominant kernel (rank 0, same process, CUDA events on the same stream) ----
     roof = None
-    e2e = None
     cpu = None
-    if rank == 0 and halo is None:
-        d = frames[0]
+    if rank == 0 and wl.halo is None:
+        d = wl.first
         plane = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         q = [d["qcoeff"][c].data_ptr() for c in range(3)]
         lf = [d["lf"][c].data_ptr() for c in range(3)]
         xyb = [plane[c].data_ptr() for c in range(3)]
-        out = [d["out"][c].data_ptr() for c in range(3)]
+        out1 = torch.empty((3, H, W), dtype=torch.float32, device=dev) if wl.stack is not None else d["out"]
+        out = [out1[c].data_ptr() for c in range(3)]
 
         def timed(fn, n=10):
             for _ in range(3):
@@ -269,11 +287,14 @@ def run_ours(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n
 
+        def stage2():
+            rec.restore_dev(p, None, xyb, W, d["hf_mul"].data_ptr(), d["sharpness"].data_ptr(), out)
+
         t1 = timed(lambda: rec.invert_dev(p, q, lf, d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
                                           d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), xyb, W))
-        t2 = timed(lambda: rec.restore_dev(p, None, xyb, W, d["hf_mul"].data_ptr(), d["sharpness"].data_ptr(), out))
+        t2 = timed(stage2)
         peak, which = peaks()
-        dom = "k2_exact (fused Gaborish+EPF+colour)" if t2 >= t1 else "stage 1 (k1_small/medium/big: dequant+CfL+LLF+IDCT)"
+        dom = "k2_exact (fused Gaborish+EPF+colour, bit-exact)" if t2 >= t1 else "stage 1 (k1_small/medium/big: dequant+CfL+LLF+IDCT)"
         bpp = BYTES_PER_PX_K2 if t2 >= t1 else BYTES_PER_PX
         ach = bpp * W * H / (max(t1, t2) / 1e3) / 1e9
         traffic = None
@@ -288,52 +309,117 @@ def run_ours(args):
                 "kernel": dom, "peak_source": which, "algorithmic_bytes_per_px": bpp,
                 "stage_ms": {"stage1_dequant_idct": t1, "stage2_gab_epf_color": t2},
                 "pipeline_frac": BYTES_PER_PX * W * H / ((t1 + t2) / 1e3) / 1e9 / peak}
+        # the tolerance mode (JXLB200_OPT_STAGE2 = 2: re-associated, FMA-contracted EPF sums; inside 1e-4 / 1 LSB at 8 bits, what a
+        # caller that quantises to 8 bits may select) timed beside the bit-exact default, with its error against it
+        if not os.environ.get("JXLB200_STAGE2"):
+            try:
+                stage2()
+                rec.sync()
+                exact = out1.clone()
+                rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_FUSED)
+                t2f = timed(stage2)
+                rec.sync()
+                err = float((out1 - exact).abs().max().item())
+                ach_f = BYTES_PER_PX_K2 * W * H / (t2f / 1e3) / 1e9
+                roof["tolerance_mode"] = {"kernel": "k2_fused (JXLB200_OPT_STAGE2 = 2)", "stage2_ms": t2f, "achieved": ach_f, "frac": ach_f / peak,
+                                          "max_abs_err_vs_exact": err,
+                                          "pipeline_frac": BYTES_PER_PX * W * H / ((t1 + t2f) / 1e3) / 1e9 / peak}
+                del exact
+            finally:
+                rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
+        del plane
 
-        # ---- e2e: the host-buffer C-ABI call a reference-side shim makes; pinned host memory, H2D + D2H inside ----
-        hst = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in
-               ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
+    # ---- e2e: the host-buffer C-ABI call a reference-side shim makes; pinned host memory, H2D + D2H inside.  EVERY rank
+    # runs it at the same time (each on its own GPU and PCIe link); the aggregate is what N GPUs deliver to N callers ----
+    e2e = None
+    if wl.halo is None and args.workload == "8k":
+        keys = ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")
+        hst = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in keys}
         hout = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
         hnp = {k: v.numpy() for k, v in hst.items()}
         houtn = hout.numpy()
         rec.set_stream(None)
-        for _ in range(2):
-            rec.reconstruct(p, hnp, out=houtn)
         n_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            rec.reconstruct(p, hnp, out=houtn)
-        dt = (time.perf_counter() - t0) / n_e2e
+
+        def wall(fn):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                fn()
+            dt = (time.perf_counter() - t0) / n_e2e
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        dt = wall(lambda: rec.reconstruct(p, hnp, out=houtn))
         h2d = sum(int(v.numel() * v.element_size()) for v in hst.values())
-        e2e = {"value": W * H / 1e6 / dt, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(hout.numel() * 4),
-               "ms_per_step": dt * 1e3, "api": "jxlb200_vardct_reconstruct (host buffers, pinned)"}
+        e2e = {"value": W * H * world / 1e6 / dt, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(hout.numel() * 4),
+               "ms_per_step": dt * 1e3, "api": "jxlb200_vardct_reconstruct (host buffers, pinned; int32 coefficients in, float32 planes out: the reference's own layout)",
+               "ranks": world, "note": "every rank makes the call at once on its own GPU; value = all ranks' pixels / slowest rank's time"}
         # the same call with the coefficients narrowed to int16 by the caller (jxlb200_vardct_reconstruct_i16: half the upload,
         # identical planes); reported beside e2e, which stays on the reference's own int32 layout
         h16 = dict(hnp)
         q16 = torch.from_numpy(np.ascontiguousarray(st["qcoeff"]).astype(np.int16)).pin_memory()
         h16["qcoeff"] = q16.numpy()
-        hout16 = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-        hout16n = hout16.numpy()
-        for _ in range(2):
-            rec.reconstruct(p, h16, out=hout16n, narrow=True)
-        same = bool(np.array_equal(hout16n, houtn))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            rec.reconstruct(p, h16, out=hout16n, narrow=True)
-        dt16 = (time.perf_counter() - t0) / n_e2e
-        e2e["int16_coefficients"] = {"value": W * H / 1e6 / dt16, "unit": "MP/s", "ms_per_step": dt16 * 1e3,
+        ref_planes = houtn.copy() if rank == 0 else None
+        dt16 = wall(lambda: rec.reconstruct(p, h16, out=houtn, narrow=True))
+        same = bool(np.array_equal(ref_planes, houtn)) if rank == 0 else None
+        e2e["int16_coefficients"] = {"value": W * H * world / 1e6 / dt16, "unit": "MP/s", "ms_per_step": dt16 * 1e3,
                                      "h2d_bytes_per_step": h2d - int(q16.numel() * 2), "planes_equal_int32_call": same,
                                      "api": "jxlb200_vardct_reconstruct_i16 (host buffers, pinned)"}
-        del q16, hout16
+        # PNG-ready samples: sRGB transfer + quantise + interleave on the device, 3 (6) bytes per pixel back
+        for bits in (8, 16):
+            hpk = torch.empty((H, W, 3 * bits // 8), dtype=torch.uint8).pin_memory()
+            hpkn = hpk.numpy()
+            dtp = wall(lambda: rec.reconstruct_packed(p, h16, bits=bits, linear=True, out=hpkn, narrow=True))
+            e2e["png%d" % bits] = {"value": W * H * world / 1e6 / dtp, "unit": "MP/s", "ms_per_step": dtp * 1e3,
+                                   "h2d_bytes_per_step": h2d - int(q16.numel() * 2), "d2h_bytes_per_step": int(hpk.numel()),
+                                   "api": "jxlb200_vardct_reconstruct_packed (int16 coefficients in, interleaved %d-bit sRGB samples out, pinned)" % bits}
+            del hpk
+        if rank == 0:
+            # what pinning buys: the same int32 / float32 call on pageable numpy arrays (a Panama Arena segment is pageable)
+            pg = {k: np.array(v, copy=True) for k, v in hnp.items()}
+            pout = np.empty((3, H, W), np.float32)
+            for _ in range(2):
+                rec.reconstruct(p, pg, out=pout)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                rec.reconstruct(p, pg, out=pout)
+            e2e["pageable_host_buffers_ms_per_step"] = (time.perf_counter() - t0) / 3 * 1e3
+            del pg, pout
+        del q16, hst, hout
         rec.set_stream(stream.cuda_stream)
 
-        if world == 1:
-            cores = os.cpu_count() or 1
-            v, dt_cpu = cpu_baseline(cores, sample=(2048, 2048), epf_iters=iters)
-            cpu = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
-                   "sample": "one 2048x2048 frame of the same synthetic workload (%.1f s), C restatement of jxlatte's algorithm, not the JVM" % dt_cpu}
+    if rank == 0 and world == 1 and wl.halo is None:
+        cores = os.cpu_count() or 1
+        v, dt_cpu = cpu_baseline(cores, sample=(2048, 2048), epf_iters=iters)
+        cpu = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": "one 2048x2048 frame of the same synthetic workload (%.1f s), C restatement of jxlatte's algorithm, not the JVM" % dt_cpu}
+
+    # ---- the other two configurations of BASELINE.json configs[4], as sub-records of the default line ----
+    sub = {}
+    if args.workload == "8k" and not args.no_sub_records:
+        names = ["batch2048"] + (["split16k"] if world > 1 else [])
+        del wl
+        torch.cuda.empty_cache()
+        for name in names:
+            try:
+                w2 = Workload(name, rec, dev, rank, world)
+                k = max(3, min(args.steps, 10))
+                ms2, _ = timed_steps(w2, stream, k, 3, barrier, dev, world)
+                sub[name] = {"value": w2.px_per_step_all * k / 1e6 / (ms2 / 1e3), "unit": "MP/s", "ms_per_step": ms2 / k, "steps": k,
+                             "scaling": "strong" if name == "split16k" else "weak",
+                             "config": workload_config(argparse.Namespace(workload=name, gpus=world), w2.iters)}
+                del w2
+                torch.cuda.empty_cache()
+            except Exception as e:      # a sub-record must never break the bench line
+                sub[name] = {"error": repr(e)}
 
     front = None
-    if rank == 0 and world == 1 and halo is None:
+    if rank == 0 and world == 1 and args.workload == "8k":
         # the sequential host half (entropy decoding, headers) is reported separately, as the north star asks: a real
         # sample through libjxlfront.so, then the same file end to end through the public JXLDecoder API on this GPU
         try:
@@ -373,6 +459,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if sub:
+            line["sub_records"] = sub
         if front:
             line["front_end"] = front
         print(json.dumps(line))
@@ -388,6 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8k", choices=["8k", "batch2048", "split16k"])
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the batch2048 / split16k sub-records of the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,6 +52,10 @@ SYMBOLS = {
     "jxlb200_vardct_reconstruct": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
     "jxlb200_vardct_reconstruct_i16": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
     "jxlb200_vardct_reconstruct_packed": (_i32, [_vp, _FP, _P3, _i32, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "jxlb200_comm_unique_id": (_i32, [_vp]),
+    "jxlb200_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "jxlb200_comm_destroy": (_i32, [_vp]),
+    "jxlb200_vardct_reconstruct_split_dev": (_i32, [_vp, _FP, C.POINTER(Slab), _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),
     "jxlb200_vardct_invert_dev": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _P3, C.c_int64]),
     "jxlb200_restore_dev": (_i32, [_vp, _FP, C.POINTER(Slab), _P3, C.c_int64, _vp, _vp, _P3]),
     "jxlb200_vardct_reconstruct_dev": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _vp, _P3]),

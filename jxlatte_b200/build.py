@@ -28,7 +28,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [NVCC] + FLAGS + ["-o", SO, os.path.join(CSRC, "jxlb200.cu"), "-lcudart"]
+    cmd = [NVCC] + FLAGS + ["-o", SO, os.path.join(CSRC, "jxlb200.cu"), "-lcudart", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)

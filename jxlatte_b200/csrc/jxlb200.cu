@@ -28,6 +28,7 @@
 #include "k8_features.cuh"
 #include "splines_host.cuh"
 #include "qm_tables.cuh"
+#include "split_nccl.cuh"
 
 // grow-only device allocation
 #ifndef JXLB200_OVERLAP_ROWS
@@ -71,6 +72,12 @@ struct jxlb200_ctx {
     DevBuf mid;        // stage-1 output planes incl. halo rows (whole path on device)
     DevBuf pp[2];      // ping-pong planes of the staged stage 2
     DevBuf in_q, in_q16, in_lf, in_maps, out_planes, mod;   // staging for the host entry points
+    // group-row split (split_nccl.cuh): communicator, its stream, the slab's stage-1 planes and block maps with room for the halos
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_halo = nullptr, ev_maps = nullptr;
+    DevBuf split_xyb, split_maps;
     DevBuf packed;          // interleaved 8/16-bit samples of jxlb200_vardct_reconstruct_packed
     DevBuf blend;           // five compact rectangles of jxlb200_blend
     DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
@@ -573,8 +580,11 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend, &ctx->packed};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend, &ctx->packed, &ctx->split_xyb, &ctx->split_maps};
     for (DevBuf *b : all) b->release();
+    if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    for (cudaEvent_t e : {ctx->ev_edge, ctx->ev_halo, ctx->ev_maps}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -772,6 +782,162 @@ int32_t jxlb200_vardct_reconstruct_batch_dev(jxlb200_ctx *ctx, const jxlb200_fra
         rc = restore_dev(ctx, p, nullptr, m3, W, hf_mul + bo_, sharpness ? sharpness + bo_ : nullptr, o3);
         if (rc) return rc;
     }
+    return 0;
+}
+
+// ---- one frame split by group rows over several GPUs (split_nccl.cuh) ----
+#define NCCL_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        ncclResult_t r__ = (expr);                                                                   \
+        if (r__ != ncclSuccess) {                                                                    \
+            (ctx)->err = std::string(#expr ": ") + nccl_api().GetErrorString(r__);                   \
+            return JXLB200_E_CUDA;                                                                   \
+        }                                                                                            \
+    } while (0)
+
+int32_t jxlb200_comm_unique_id(uint8_t id[JXLB200_COMM_ID_BYTES]) {
+    if (!id) return JXLB200_E_ARG;
+    if (!nccl_api().ok) return JXLB200_E_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == JXLB200_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    if (nccl_api().GetUniqueId(&u) != ncclSuccess) return JXLB200_E_CUDA;
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int32_t jxlb200_comm_init(jxlb200_ctx *ctx, const uint8_t id[JXLB200_COMM_ID_BYTES], int32_t rank, int32_t world) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!id || world < 1 || rank < 0 || rank >= world) return ctx->fail(JXLB200_E_ARG, "bad communicator arguments");
+    if (!nccl_api().ok) return ctx->fail(JXLB200_E_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NCCL_TRY(ctx, nccl_api().CommInitRank(&ctx->comm, world, u, rank));
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    if (!ctx->comm_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_edge, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_maps, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int32_t jxlb200_comm_destroy(jxlb200_ctx *ctx) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->comm_world = 1; ctx->comm_rank = 0;
+    return 0;
+}
+
+int32_t jxlb200_vardct_reconstruct_split_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_slab *slab,
+    const int32_t *const qcoeff[3], const float *const lf[3],
+    const uint8_t *dct_select, const uint8_t *block_origin, const int32_t *hf_mul,
+    const int32_t *x_from_y, const int32_t *b_from_y, const int32_t *sharpness, float *const out[3]) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!slab || !qcoeff || !lf || !dct_select || !block_origin || !hf_mul || !x_from_y || !b_from_y || !sharpness || !out)
+        return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    if (is_subsampled(p)) return ctx->fail(JXLB200_E_UNSUPPORTED, "group-row split of chroma-subsampled frames");
+    const int W = p->width, R = p->height, wb = W >> 3, tw = (W + 63) >> 6;
+    if (slab->rows != R || (slab->y0 & 255) || slab->y0 + R > slab->frame_height || (R & 7))
+        return ctx->fail(JXLB200_E_ARG, "slab must start on a group row, match p->height and stay inside the frame");
+    const bool up = slab->has_top != 0, down = slab->has_bottom != 0;
+    if ((up || down) && !ctx->comm) return ctx->fail(JXLB200_E_ARG, "jxlb200_comm_init has not been called");
+    if ((up && ctx->comm_rank == 0) || (down && ctx->comm_rank == ctx->comm_world - 1))
+        return ctx->fail(JXLB200_E_ARG, "slab has a neighbour where the communicator has no rank");
+    if ((up || down) && R < 2 * JXLB200_HALO_ROWS) return ctx->fail(JXLB200_E_ARG, "slab shorter than its two halos");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int HR = JXLB200_HALO_ROWS;
+    const size_t plane = (size_t)(R + 2 * HR) * W, mrows = (size_t)(R / 8 + 2) * wb;
+    CUDA_TRY(ctx, ctx->split_xyb.ensure(sizeof(float) * 3 * plane));
+    CUDA_TRY(ctx, ctx->split_maps.ensure(sizeof(int32_t) * 2 * mrows));
+    float *xyb[3];
+    for (int c = 0; c < 3; c++) xyb[c] = ctx->split_xyb.as<float>() + c * plane + (size_t)HR * W;     // row 0 of the slab
+    int32_t *hm = ctx->split_maps.as<int32_t>() + wb, *sh = hm + mrows;                                 // block row 0 of the slab
+    cudaStream_t main = ctx->stream, cs = ctx->comm_stream;
+    NcclApi &N = nccl_api();
+
+    // block maps with one neighbour block row each side (a frame edge keeps benign values there: nothing reads them)
+    CUDA_TRY(ctx, cudaMemcpyAsync(hm, hf_mul, sizeof(int32_t) * (size_t)(R / 8) * wb, cudaMemcpyDeviceToDevice, main));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sh, sharpness, sizeof(int32_t) * (size_t)(R / 8) * wb, cudaMemcpyDeviceToDevice, main));
+    if (!up) { CUDA_TRY(ctx, cudaMemsetAsync(hm - wb, 0, sizeof(int32_t) * wb, main)); CUDA_TRY(ctx, cudaMemsetAsync(sh - wb, 0, sizeof(int32_t) * wb, main)); }
+    if (!down) { CUDA_TRY(ctx, cudaMemsetAsync(hm + (size_t)(R / 8) * wb, 0, sizeof(int32_t) * wb, main)); CUDA_TRY(ctx, cudaMemsetAsync(sh + (size_t)(R / 8) * wb, 0, sizeof(int32_t) * wb, main)); }
+
+    auto stage1 = [&](int y0, int rows) -> int {           // group rows [y0, y0 + rows) of the slab
+        if (rows <= 0) return 0;
+        jxlb200_frame_params ps = *p;
+        ps.height = rows;
+        const size_t off = (size_t)y0 * W, bo_ = (size_t)(y0 / 8) * wb, to = (size_t)(y0 / 64) * tw;
+        const int32_t *q3[3] = {qcoeff[0] + off, qcoeff[1] + off, qcoeff[2] + off};
+        const float *l3[3] = {lf[0] + bo_, lf[1] + bo_, lf[2] + bo_};
+        float *m3[3] = {xyb[0] + off, xyb[1] + off, xyb[2] + off};
+        return invert_dev(ctx, &ps, q3, l3, dct_select + bo_, block_origin + bo_, hf_mul + bo_, x_from_y + to, b_from_y + to, m3, W);
+    };
+    auto stage2 = [&](int a, int b, bool top_nb, bool bottom_nb) -> int {      // rows [a, b) of the slab
+        if (b <= a) return 0;
+        jxlb200_frame_params ps = *p;
+        ps.height = b - a;
+        jxlb200_slab sl = {slab->y0 + a, b - a, slab->frame_height, top_nb ? 1 : 0, bottom_nb ? 1 : 0};
+        const float *m3[3] = {xyb[0] + (size_t)a * W, xyb[1] + (size_t)a * W, xyb[2] + (size_t)a * W};
+        float *o3[3] = {out[0] + (size_t)a * W, out[1] + (size_t)a * W, out[2] + (size_t)a * W};
+        return restore_dev(ctx, &ps, &sl, m3, W, hm + (size_t)(a / 8) * wb, sh + (size_t)(a / 8) * wb, o3);
+    };
+
+    if (!up && !down) {                                     // a "split" over one rank
+        if ((rc = stage1(0, R))) return rc;
+        return stage2(0, R, false, false);
+    }
+    // 1. the boundary group rows first
+    const int G = 256;
+    const bool edges_first = R >= 3 * G;
+    if (edges_first) {
+        if ((rc = stage1(0, G))) return rc;
+        const int last0 = ((R - 1) / G) * G;                // first row of the last (possibly short) group row
+        if ((rc = stage1(last0, R - last0))) return rc;
+    } else if ((rc = stage1(0, R))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_edge, main));
+    // 2. halo rows and the neighbours' block rows, one NCCL group on the comm stream
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_edge, 0));
+    NCCL_TRY(ctx, N.GroupStart());
+    const size_t hn = (size_t)HR * W;
+    for (int c = 0; c < 3; c++) {
+        if (up) {
+            NCCL_TRY(ctx, N.Send(xyb[c], hn, ncclFloat, ctx->comm_rank - 1, ctx->comm, cs));                          // my first rows
+            NCCL_TRY(ctx, N.Recv(xyb[c] - hn, hn, ncclFloat, ctx->comm_rank - 1, ctx->comm, cs));                     // its last rows
+        }
+        if (down) {
+            NCCL_TRY(ctx, N.Send(xyb[c] + (size_t)(R - HR) * W, hn, ncclFloat, ctx->comm_rank + 1, ctx->comm, cs));    // my last rows
+            NCCL_TRY(ctx, N.Recv(xyb[c] + (size_t)R * W, hn, ncclFloat, ctx->comm_rank + 1, ctx->comm, cs));           // its first rows
+        }
+    }
+    for (int32_t *m : {hm, sh}) {
+        if (up) {
+            NCCL_TRY(ctx, N.Send(m, wb, ncclInt32, ctx->comm_rank - 1, ctx->comm, cs));
+            NCCL_TRY(ctx, N.Recv(m - wb, wb, ncclInt32, ctx->comm_rank - 1, ctx->comm, cs));
+        }
+        if (down) {
+            NCCL_TRY(ctx, N.Send(m + (size_t)(R / 8 - 1) * wb, wb, ncclInt32, ctx->comm_rank + 1, ctx->comm, cs));
+            NCCL_TRY(ctx, N.Recv(m + (size_t)(R / 8) * wb, wb, ncclInt32, ctx->comm_rank + 1, ctx->comm, cs));
+        }
+    }
+    NCCL_TRY(ctx, N.GroupEnd());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_halo, cs));
+    // 3. the rest of stage 1 and the rows of stage 2 that need no halo, beside the exchange
+    if (edges_first) {
+        const int last0 = ((R - 1) / G) * G;
+        if ((rc = stage1(G, last0 - G))) return rc;
+    }
+    const int a = up ? HR : 0, b = down ? R - HR : R;
+    if ((rc = stage2(a, b, up, down))) return rc;
+    // 4. the rows next to the neighbours
+    CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_halo, 0));
+    if (up && (rc = stage2(0, HR, true, true))) return rc;
+    if (down && (rc = stage2(R - HR, R, true, true))) return rc;
+    // the next call's stage 1 overwrites rows the comm stream may still be sending from only after this event
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_maps, main));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_maps, 0));
     return 0;
 }
 

@@ -264,6 +264,29 @@ class Reconstructor:
         self._check(self._L.jxlb200_vardct_reconstruct_batch_dev(self._h, C.byref(p), int(n_frames), _lib.planes(q), _lib.planes(lf),
                                                                  ds, bo, hm, xf, bf, sh, _lib.planes(out)))
 
+    # -- one frame split by group rows over the GPUs of a box (jxlb200_comm_* / ..._split_dev) --
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes made by rank 0 (ncclGetUniqueId) and handed to every rank's comm_init."""
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.lib().jxlb200_comm_unique_id(buf)
+        if rc:
+            raise (NotImplementedError if rc == _lib.E_UNSUPPORTED else RuntimeError)("jxlb200_comm_unique_id: status %d" % rc)
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._L.jxlb200_comm_init(self._h, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._L.jxlb200_comm_destroy(self._h))
+
+    def reconstruct_split_dev(self, p, slab, q, lf, ds, bo, hm, xf, bf, sh, out):
+        """This rank's slab of a frame split by group rows: stage 1, NCCL halo rows (overlapped), stage 2.  Device pointers of
+        the slab's own rows only."""
+        self._check(self._L.jxlb200_vardct_reconstruct_split_dev(self._h, C.byref(p), C.byref(slab), _lib.planes(q), _lib.planes(lf),
+                                                                 ds, bo, hm, xf, bf, sh, _lib.planes(out)))
+
     def invert_dev(self, p, q, lf, ds, bo, hm, xf, bf, xyb, pitch):
         self._check(self._L.jxlb200_vardct_invert_dev(self._h, C.byref(p), _lib.planes(q), _lib.planes(lf), ds, bo, hm, xf, bf,
                                                       _lib.planes(xyb), int(pitch)))

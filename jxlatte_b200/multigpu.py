@@ -4,9 +4,10 @@ Two ways the path shards, exactly as the north star states:
   * a batch of frames: frame i goes to rank i % world -- no communication at all (bench.py --workload 8k / batch2048);
   * one very large frame: contiguous GROUP ROWS (256 px) per rank.  Stage 1 needs nothing from the neighbours (varblocks
     never cross a group boundary); stage 2 needs JXLB200_HALO_ROWS rows of the neighbours' stage-1 output above and below
-    (Gaborish 1 + EPF 3 + 2 + 1 = 7 used) plus one block row of hf_mul / sharpness, exchanged point-to-point with
-    torch.distributed (NCCL over NVLink on GPUs; the same code runs on gloo/CPU tensors in the tests).  The true frame
-    top and bottom mirror inside the kernel instead.
+    (Gaborish 1 + EPF 3 + 2 + 1 = 7 used) plus one block row of hf_mul / sharpness.  On GPUs the exchange is inside the
+    library (jxlb200_vardct_reconstruct_split_dev: ncclSend / ncclRecv over NVLink on a side stream, overlapped with the
+    slab's own work); exchange_halos() below is the same hand-over on torch.distributed tensors, kept for the gloo/CPU
+    tests of the row arithmetic.  The true frame top and bottom mirror inside the kernel instead.
 """
 import numpy as np
 
@@ -63,42 +64,33 @@ def exchange_halos(ext, halo, rank, world, group=None):
 
 
 class SplitFrame:
-    """One rank's slab of a frame split by group rows; step() = stage 1, halo exchange, stage 2."""
+    """One rank's slab of a frame split by group rows; step() = stage 1, halo rows to / from the neighbours, stage 2.
+
+    The whole step is ONE C-ABI call, jxlb200_vardct_reconstruct_split_dev: the library owns the communicator (NCCL, joined
+    here with an id rank 0 makes and torch.distributed merely carries to the other ranks), sends the boundary rows on its own
+    stream right after the boundary group rows' stage 1 and runs the rest of the slab meanwhile (csrc/split_nccl.cuh).  It
+    enqueues on the Reconstructor's stream; bind that to the stream the caller times or synchronises (rec.set_stream)."""
 
     def __init__(self, rec, p_slab, dev_state, y0, rows, frame_height, rank, world, device):
         import torch
+        import torch.distributed as dist
         self.rec, self.p, self.d = rec, p_slab, dev_state
         self.rank, self.world = rank, world
-        W = p_slab.width
-        self.W, self.rows = W, rows
         self.slab = Slab(y0, rows, frame_height, 1 if rank > 0 else 0, 1 if rank < world - 1 else 0)
-        # stage-1 output with HALO_ROWS spare rows above and below, so stage 2 addresses neighbours' rows uniformly
-        self.xyb = torch.zeros((3, rows + 2 * HALO_ROWS, W), dtype=torch.float32, device=device)
-        wb = W // 8
-        self.maps = torch.zeros((2, rows // 8 + 2, wb), dtype=torch.int32, device=device)
-        self.maps[0, 1:-1].copy_(dev_state["hf_mul"])
-        self.maps[1, 1:-1].copy_(dev_state["sharpness"])
-        if world > 1:
-            exchange_halos(self.maps, 1, rank, world)
-        # a frame edge has no neighbour: give the unused extra block row benign values
-        if rank == 0:
-            self.maps[:, 0].fill_(1)
-        if rank == world - 1:
-            self.maps[:, -1].fill_(1)
         self.out = dev_state["out"]
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device=device)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(rec.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            rec.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
     def step(self):
-        d, W = self.d, self.W
-        esz = 4
-        base = [self.xyb[c].data_ptr() + HALO_ROWS * W * esz for c in range(3)]
-        self.rec.invert_dev(self.p, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
-                            d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
-                            d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), base, W)
-        if self.world > 1:
-            exchange_halos(self.xyb, HALO_ROWS, self.rank, self.world)
-        wb = W // 8
-        self.rec.restore_dev(self.p, self.slab, base, W, self.maps[0].data_ptr() + wb * esz, self.maps[1].data_ptr() + wb * esz,
-                             [self.out[c].data_ptr() for c in range(3)])
+        d = self.d
+        self.rec.reconstruct_split_dev(self.p, self.slab, [d["qcoeff"][c].data_ptr() for c in range(3)],
+                                       [d["lf"][c].data_ptr() for c in range(3)], d["dct_select"].data_ptr(), d["block_origin"].data_ptr(),
+                                       d["hf_mul"].data_ptr(), d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
+                                       [self.out[c].data_ptr() for c in range(3)])
 
 
 def split_state(st, y0, rows):

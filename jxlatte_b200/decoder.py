@@ -27,6 +27,24 @@ FLAG_NOISE, FLAG_PATCHES, FLAG_SPLINES, FLAG_USE_LF_FRAME = 1, 2, 16, 32
 TF_SRGB, TF_LINEAR = (1 << 24) + 13, (1 << 24) + 8
 
 
+class JXLOptions:
+    """The reference's JXLOptions (J/JXLOptions.java:7-50), the fields that reach the reconstruction path."""
+    OUTPUT_DEFAULT, OUTPUT_PNG, OUTPUT_PFM = -1, 0, 1
+
+    def __init__(self, outputFormat=-1, outputDepth=-1):
+        self.outputFormat = outputFormat    # OUTPUT_PNG: the caller will quantise with PNGWriter; OUTPUT_PFM / default: float samples
+        self.outputDepth = outputDepth      # -1: PNGWriter picks 8 for images of up to 8 bits per sample, else 16
+
+    def quantises_to_8_bits(self, bits_per_sample):
+        """True when the only consumer of the planes is PNGWriter at 8 bits: the tolerance "<= 1e-4 and <= 1 LSB" of the north
+        star is then met by the re-associated filter sums too, and the engine may use them (JXLB200_OPT_STAGE2 = 2).  16-bit PNG
+        and PFM output keep the bit-exact kernels (profiles/r2_exact_vs_fast.md has the price of each)."""
+        if self.outputFormat != self.OUTPUT_PNG:
+            return False
+        depth = self.outputDepth if self.outputDepth > 0 else (8 if bits_per_sample <= 8 else 16)
+        return depth <= 8
+
+
 class CudaEngine:
     """The product back end: every data-parallel stage on the GPU through the C ABI."""
 
@@ -36,6 +54,7 @@ class CudaEngine:
         self.rec = host.Reconstructor(device)
         self._qm_default = None
         self._uploaded = None
+        self.tolerance_mode = False         # set per image by JXLDecoder from JXLOptions
 
     def qm_default(self):
         if self._qm_default is None:        # HFGlobal.defaultParams tables: built once, shared by every frame that uses them
@@ -52,7 +71,14 @@ class CudaEngine:
         if st["qm_weights"] is not self._uploaded:      # same table object as the previous frame: already on the device
             self.rec.setWeights(st["qm_weights"], st["qm_offsets"])
             self._uploaded = st["qm_weights"]
-        return self.rec.reconstruct(p, st)
+        if not self.tolerance_mode:
+            return self.rec.reconstruct(p, st)
+        from . import _lib
+        self.rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_FUSED)
+        try:
+            return self.rec.reconstruct(p, st)
+        finally:
+            self.rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
 
     def modular(self, channels, transforms, bit_depth):
         return self._host.ModularTransforms(self.rec, bit_depth).applyTransforms(channels, transforms)
@@ -214,7 +240,8 @@ class JXLImage:
 
 
 class JXLDecoder:
-    def __init__(self, source, engine=None):
+    def __init__(self, source, engine=None, options=None):
+        self.options = options if options is not None else JXLOptions()
         if isinstance(source, (bytes, bytearray, memoryview)):
             self.data = bytes(source)
         elif isinstance(source, str):
@@ -474,6 +501,8 @@ class JXLDecoder:
         if self.engine is None:
             self.engine = CudaEngine()
         info = parsed.info
+        if hasattr(self.engine, "tolerance_mode"):
+            self.engine.tolerance_mode = self.options.quantises_to_8_bits(info["bits_per_sample"])
         colors, nextra = info["color_channels"], len(info["extra_channels"])
         canvas = None                      # list of _Buf
         reference = [None, None, None, None]

@@ -416,3 +416,20 @@ def test_container_box_size_overflow_is_rejected():
         evil = struct.pack(">I4sQ", 1, tag, 0xFFFFFFFFFFFFFFF8)
         with pytest.raises(Exception):
             frontend.parse(sig + free8 + evil)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lenna", "bbb"])
+def test_tolerance_mode_for_8_bit_png_output(name):
+    """JXLOptions(outputFormat=PNG, outputDepth=8): the decoder may use the re-associated stage 2 (JXLB200_OPT_STAGE2 = 2); the
+    north star's tolerance is what it is held to -- 1e-4 on the linear planes, 1 LSB on the 8-bit samples -- against the bit-exact
+    decode.  Any other output keeps the bit-exact kernels."""
+    from jxlatte_b200.decoder import JXLOptions
+    path = os.path.join(S, name + ".jxl")
+    exact = JXLDecoder(path).decode()
+    fast = JXLDecoder(path, options=JXLOptions(JXLOptions.OUTPUT_PNG, 8)).decode()
+    assert float(np.abs(fast.planes - exact.planes).max()) <= 1e-4
+    assert int(np.abs(fast.to_int(8).astype(np.int64) - exact.to_int(8).astype(np.int64)).max()) <= 1
+    assert not np.array_equal(fast.planes, exact.planes)          # it really took the other kernel
+    for opts in (JXLOptions(JXLOptions.OUTPUT_PNG, 16), JXLOptions(JXLOptions.OUTPUT_PFM), JXLOptions()):
+        assert np.array_equal(JXLDecoder(path, options=opts).decode().planes, exact.planes)

@@ -78,6 +78,7 @@ struct jxlb200_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_halo = nullptr, ev_maps = nullptr;
     DevBuf split_xyb, split_maps;
+    DevBuf pack_thr[4];     // threshold tables of the sample pipeline: (8 | 16 bits) x (as is | sRGB from linear)
     DevBuf packed;          // interleaved 8/16-bit samples of jxlb200_vardct_reconstruct_packed
     DevBuf blend;           // five compact rectangles of jxlb200_blend
     DevBuf sub, sub_maps;   // chroma-subsampled frames: per-channel planes + scratch, strided block maps
@@ -580,7 +581,7 @@ void jxlb200_destroy(jxlb200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->sched, &ctx->items, &ctx->gate, &ctx->wraw, &ctx->woff, &ctx->wexp, &ctx->cosbig, &ctx->lut8, &ctx->sigma, &ctx->flags,
-                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend, &ctx->packed, &ctx->split_xyb, &ctx->split_maps};
+                     &ctx->mid, &ctx->pp[0], &ctx->pp[1], &ctx->in_q, &ctx->in_q16, &ctx->in_lf, &ctx->in_maps, &ctx->out_planes, &ctx->mod, &ctx->sub, &ctx->sub_maps, &ctx->blend, &ctx->packed, &ctx->split_xyb, &ctx->split_maps, &ctx->pack_thr[0], &ctx->pack_thr[1], &ctx->pack_thr[2], &ctx->pack_thr[3]};
     for (DevBuf *b : all) b->release();
     if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -1054,14 +1055,28 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
     for (int c = 0; c < 3; c++)
         if (!qcoeff[c] || !lf[c] || (!pk && !out[c])) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
     const size_t pk_row = pk ? (size_t)pk->crop_w * 3 * (pk->bits > 8 ? 2 : 1) : 0;
-    if (pk) CUDA_TRY(ctx, ctx->packed.ensure(pk_row * pk->crop_h + 64));
+    const float *pk_thr = nullptr;
+    if (pk) {
+        CUDA_TRY(ctx, ctx->packed.ensure(pk_row * pk->crop_h + 64));
+        // the sample pipeline as a threshold table (k8_features.cuh), one per (bits, linear), built on first use
+        const int slot = (pk->bits > 8 ? 2 : 0) + (pk->linear ? 1 : 0);
+        if (!ctx->pack_thr[slot].p) {
+            std::vector<float> thr;
+            pack_thresholds(pk->bits, pk->linear, thr);
+            thr.resize((size_t)1 << pk->bits, INFINITY);        // the 16-bit search reads whole 256-entry segments
+            CUDA_TRY(ctx, ctx->pack_thr[slot].ensure(sizeof(float) * thr.size()));
+            CUDA_TRY(ctx, cudaMemcpy(ctx->pack_thr[slot].p, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice));
+        }
+        pk_thr = ctx->pack_thr[slot].as<float>();
+    }
     // rows [a, b) of the device planes -> packed samples -> host, on stream st (enqueued after stage 2 of those rows)
     auto send_packed = [&](float *const dplanes[3], int a, int b, cudaStream_t kst, cudaStream_t cst, cudaEvent_t ev) -> int {
         b = b < pk->crop_h ? b : pk->crop_h;
         if (a >= b) return 0;
         const long long quads = (long long)(b - a) * ((pk->crop_w + 3) >> 2);
         const int grid = (int)(quads / 256 + 1 < (long long)ctx->sms * 8 ? quads / 256 + 1 : (long long)ctx->sms * 8);
-        k8_pack_rgb<<<grid, 256, 0, kst>>>(dplanes[0], dplanes[1], dplanes[2], p->width, a, b, pk->crop_w, pk->linear, pk->bits, ctx->packed.as<unsigned char>());
+        if (pk->bits == 8) k8_pack_rgb<8><<<grid, 256, 0, kst>>>(dplanes[0], dplanes[1], dplanes[2], p->width, a, b, pk->crop_w, pk_thr, ctx->packed.as<unsigned char>());
+        else k8_pack_rgb<16><<<grid, 256, 0, kst>>>(dplanes[0], dplanes[1], dplanes[2], p->width, a, b, pk->crop_w, pk_thr, ctx->packed.as<unsigned char>());
         ctx->launches++;
         if (kst != cst) { cudaEventRecord(ev, kst); cudaStreamWaitEvent(cst, ev, 0); }
         cudaError_t e = cudaMemcpyAsync(pk->dst + pk_row * a, ctx->packed.as<unsigned char>() + pk_row * a, pk_row * (b - a), cudaMemcpyDeviceToHost, cst);

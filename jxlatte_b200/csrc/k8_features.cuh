@@ -246,19 +246,81 @@ __global__ void k8_pack_samples(PackArgs A) {
 // ---- the same conversion for the three colour planes of a VarDCT frame, rows [r0, r1) x columns [0, cw) of planes with
 // pitch `pitch`, straight after stage 2 on the device: what the pipelined host entry point sends back instead of 12 bytes of
 // float per pixel (jxlb200_vardct_reconstruct_packed).  Four pixels per thread: three 128-bit loads, 12 or 24 bytes out.
-__device__ __forceinline__ int pack_one(float v, int linear, int maxv) {
-    if (linear) {       // TF_SRGB.fromLinearF, J/color/TransferFunction.java:39-43
-        if (v < 0.00313066844250063f) v = __fmul_rn(v, 12.92f);
-        else v = __fadd_rn(__fmul_rn(1.055f, (float)pow((double)v, 0.4166666666666667)), -0.055f);
+//
+// The reference's sample pipeline -- TF_SRGB.fromLinearF with (float)Math.pow(double) (J/color/TransferFunction.java:39-43), then
+// (int)(v * max + 0.5f) and a clamp (J/util/ImageBuffer.java:129-145) -- is a MONOTONE step function of the float v: every stage
+// is non-decreasing in float arithmetic.  So it is exactly a table of thresholds, thr[k] = the smallest float whose sample is
+// >= k, built once on the host by bisection over float bit patterns WITH the reference's formula (pack_sample_ref below), and the
+// device only counts thresholds <= v (binary search): bit-identical to evaluating the formula, without a double-precision pow
+// per sample (which made this kernel, not PCIe, the limit of the packed call: 100 M pows per 8K frame).
+static inline int pack_sample_ref(float v, int linear, int maxv) {
+    if (v != v) return 0;
+    if (linear) {
+        if (v < 0.00313066844250063f) v = v * 12.92f;
+        else v = 1.055f * (float)pow((double)v, 0.4166666666666667) + -0.055f;
     }
-    int q = java_f2i(__fadd_rn(__fmul_rn(v, (float)maxv), 0.5f));      // ImageBuffer.castToIntWithMax, J/util/ImageBuffer.java:129-145
-    return q < 0 ? 0 : (q > maxv ? maxv : q);
+    const float f = v * (float)maxv + 0.5f;
+    if (f != f) return 0;
+    long long q = f >= 2147483648.0f ? 2147483647ll : (f <= -2147483648.0f ? -2147483648ll : (long long)f);   // the JVM's (int) cast
+    return q < 0 ? 0 : (q > maxv ? maxv : (int)q);
 }
+// floats ordered as integers: key(v) increases with v over all non-NaN floats
+static inline uint32_t float_key(float v) { uint32_t u; memcpy(&u, &v, 4); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+static inline float key_float(uint32_t k) { uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; float v; memcpy(&v, &u, 4); return v; }
+// thr[k - 1], k = 1 .. maxv: the smallest float v with pack_sample_ref(v) >= k (+inf when no float reaches k)
+static inline void pack_thresholds(int bits, int linear, std::vector<float> &thr) {
+    const int maxv = (1 << bits) - 1;
+    thr.resize(maxv);
+    const uint32_t kmin = float_key(-INFINITY), kmax = float_key(INFINITY);
+    uint32_t from = kmin;
+    for (int k = 1; k <= maxv; k++) {
+        uint32_t lo = from, hi = kmax;                      // invariant: sample(lo) < k or lo == from; answer in (lo, hi]
+        if (pack_sample_ref(key_float(hi), linear, maxv) < k) { thr[k - 1] = INFINITY; continue; }
+        if (pack_sample_ref(key_float(lo), linear, maxv) >= k) { thr[k - 1] = key_float(lo); continue; }
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (pack_sample_ref(key_float(mid), linear, maxv) >= k) hi = mid; else lo = mid;
+        }
+        thr[k - 1] = key_float(hi);
+        from = hi;
+    }
+}
+
+// number of thresholds <= v = the sample; NaN compares false everywhere -> 0, like the JVM's (int) cast
+template <int BITS> __device__ __forceinline__ int pack_search(const float *__restrict__ coarse, const float *__restrict__ thr, float v) {
+    constexpr int MAXV = (1 << BITS) - 1;
+    if (BITS == 8) {
+        int lo = 0;                                         // thresholds [0, 255) in shared memory
+#pragma unroll
+        for (int step = 128; step >= 1; step >>= 1)
+            if (lo + step <= MAXV && coarse[lo + step - 1] <= v) lo += step;
+        return lo;
+    } else {
+        // coarse[j] = thr[256 j + 255] (shared memory): first the 256-sample segment, then inside it (global, one or two lines)
+        int seg = 0;
+#pragma unroll
+        for (int step = 128; step >= 1; step >>= 1)
+            if (seg + step <= 255 && coarse[seg + step - 1] <= v) seg += step;
+        // seg = number of coarse thresholds <= v: the answer lies in [256 seg, 256 seg + 255]
+        const float *t = thr + 256 * seg;
+        int lo = 0;
+#pragma unroll
+        for (int step = 128; step >= 1; step >>= 1)
+            if (256 * seg + lo + step <= MAXV && __ldg(t + lo + step - 1) <= v) lo += step;
+        return 256 * seg + lo;
+    }
+}
+
+template <int BITS>
 __global__ void k8_pack_rgb(const float *__restrict__ p0, const float *__restrict__ p1, const float *__restrict__ p2, long long pitch,
-                            int r0, int r1, int cw, int linear, int bits, unsigned char *__restrict__ out) {
+                            int r0, int r1, int cw, const float *__restrict__ thr, unsigned char *__restrict__ out) {
+    __shared__ float coarse[256];
+    if (BITS == 8) { for (int i = threadIdx.x; i < 255; i += blockDim.x) coarse[i] = thr[i]; }
+    else { for (int i = threadIdx.x; i < 255; i += blockDim.x) coarse[i] = thr[256 * i + 255]; }
+    __syncthreads();
     const int quads = (cw + 3) >> 2;
     const long long n = (long long)(r1 - r0) * quads;
-    const int maxv = (1 << bits) - 1, bytes = bits > 8 ? 2 : 1;
+    constexpr int bytes = BITS > 8 ? 2 : 1;
     const bool vec = (pitch & 3) == 0 && ((((size_t)p0 | (size_t)p1 | (size_t)p2) & 15) == 0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int r = r0 + (int)(i / quads), x = 4 * (int)(i % quads);
@@ -274,7 +336,7 @@ __global__ void k8_pack_rgb(const float *__restrict__ p0, const float *__restric
         }
         unsigned char *dst = out + ((long long)r * cw + x) * 3 * bytes;
         for (int k = 0; k < nv; k++) {
-            const int q[3] = {pack_one(a[k], linear, maxv), pack_one(b[k], linear, maxv), pack_one(c[k], linear, maxv)};
+            const int q[3] = {pack_search<BITS>(coarse, thr, a[k]), pack_search<BITS>(coarse, thr, b[k]), pack_search<BITS>(coarse, thr, c[k])};
             for (int ch = 0; ch < 3; ch++) {
                 if (bytes == 2) { dst[(3 * k + ch) * 2] = (unsigned char)(q[ch] >> 8); dst[(3 * k + ch) * 2 + 1] = (unsigned char)(q[ch] & 255); }   // PNG is big endian
                 else dst[3 * k + ch] = (unsigned char)q[ch];

@@ -48,12 +48,16 @@ class JXLOptions:
 class CudaEngine:
     """The product back end: every data-parallel stage on the GPU through the C ABI."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, allow_tolerance_mode=False):
+        """allow_tolerance_mode: let JXLOptions(OUTPUT_PNG, 8) select the re-associated stage 2 (JXLB200_OPT_STAGE2 = 2).  OFF by
+        default: measured on B200 that kernel (k2_fused) is inside the tolerance but SLOWER than the bit-exact k2_exact (2.40 vs
+        1.79 ms per 8K frame, profiles/r2_exact_vs_fast.md), so there is nothing to buy with the error yet."""
         from . import host
         self._host = host
         self.rec = host.Reconstructor(device)
         self._qm_default = None
         self._uploaded = None
+        self.allow_tolerance_mode = allow_tolerance_mode
         self.tolerance_mode = False         # set per image by JXLDecoder from JXLOptions
 
     def qm_default(self):
@@ -71,7 +75,7 @@ class CudaEngine:
         if st["qm_weights"] is not self._uploaded:      # same table object as the previous frame: already on the device
             self.rec.setWeights(st["qm_weights"], st["qm_offsets"])
             self._uploaded = st["qm_weights"]
-        if not self.tolerance_mode:
+        if not (self.tolerance_mode and self.allow_tolerance_mode):
             return self.rec.reconstruct(p, st)
         from . import _lib
         self.rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_FUSED)

@@ -63,6 +63,7 @@ SYMBOLS = {
     "jxlb200_host_slab_schedule": (_i32, [_i32, _vp, _i32]),
     "jxlb200_host_stage2_ranges": (_i32, [_i32, _vp, _vp, _i32]),
     "jxlb200_gaborish": (_i32, [_vp, _FP, _P3, _P3]),
+    "jxlb200_restore_uniform": (_i32, [_vp, _FP, C.c_float, _P3, _P3]),
     "jxlb200_epf": (_i32, [_vp, _FP, _P3, _vp, _vp, _P3]),
     "jxlb200_color_transform": (_i32, [_vp, _FP, _P3, _P3]),
     "jxlb200_vardct_invert": (_i32, [_vp, _FP, _P3, _P3, _vp, _vp, _vp, _vp, _vp, _P3]),

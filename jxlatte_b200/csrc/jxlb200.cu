@@ -62,6 +62,8 @@ struct jxlb200_ctx {
     int64_t launches = 0;
     bool have_weights = false;
     int opt_stage2 = 0;
+    bool uniform_sigma = false;         // jxlb200_restore_uniform: one 1/sigma for every block instead of the hf_mul / sharpness maps
+    float uniform_inv_sigma = 0.0f;
     int opt_overlap_rows = JXLB200_OVERLAP_ROWS;   // device-resident whole path: slab height for overlapping stage 2 of slab j with stage 1 of slab j+2 (0 = off)
     std::vector<cudaEvent_t> ev_pool;
 
@@ -350,7 +352,7 @@ void fill_k2(K2Params &K, const jxlb200_frame_params *p, const jxlb200_slab *sla
     K.frame_h = slab ? slab->frame_height : p->height;
     K.has_top = slab ? slab->has_top : 0;
     K.has_bottom = slab ? slab->has_bottom : 0;
-    K.wb = p->width >> 3;
+    K.wb = (p->width + 7) >> 3;          // Modular frames are not padded to 8 (Frame.getPaddedFrameSize :924-941)
     K.gab = p->gab; K.iters = p->epf_iters; K.color_mode = p->color_mode;
     for (int c = 0; c < 3; c++) {   // Frame.performGabConvolution :510-517
         const float w1 = p->gab_w1[c], w2 = p->gab_w2[c];
@@ -387,7 +389,7 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
     // inverse sigma per block, with one extra block row towards each neighbour slab
     float *inv_sigma = nullptr;
     if (K.iters > 0) {
-        CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * ((size_t)(rows / 8) * n_frames + 2)));
+        CUDA_TRY(ctx, ctx->sigma.ensure(sizeof(float) * (size_t)wb * ((size_t)((rows + 7) / 8) * n_frames + 2)));
         CUDA_TRY(ctx, ctx->lut8.ensure(sizeof(float) * 8));
         if (!ctx->flags.p) {
             CUDA_TRY(ctx, ctx->flags.ensure(sizeof(int) * 4));
@@ -403,9 +405,12 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
             ctx->lut8_valid = true;
         }
         inv_sigma = ctx->sigma.as<float>() + wb;
-        const int br0 = K.has_top ? -1 : 0, br1 = (rows / 8) * n_frames + (K.has_bottom ? 1 : 0);
-        k2_sigma<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(hf_mul, sharp, wb, br0, br1, K.gscale,
-                                                                                     ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
+        const int br0 = K.has_top ? -1 : 0, br1 = ((rows + 7) / 8) * n_frames + (K.has_bottom ? 1 : 0);
+        if (ctx->uniform_sigma)
+            k2_sigma_fill<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(ctx->uniform_inv_sigma, (long long)br0 * wb, (long long)(br1 - br0) * wb, inv_sigma);
+        else
+            k2_sigma<<<min(ctx->sms * 2, ceil_div((br1 - br0) * wb, 256)), 256, 0, st>>>(hf_mul, sharp, wb, br0, br1, K.gscale,
+                                                                                         ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
 #ifdef JXLB200_WITH_STREAM
@@ -1288,6 +1293,42 @@ static int host_stage(jxlb200_ctx *ctx, const jxlb200_frame_params *p, int mode,
     rc = restore_dev(ctx, &q, nullptr, (const float *const *)din, p->width, M.hf, M.sharp, dout);
     if (rc) return rc;
     return stage_out_planes(ctx, dout, sizeof(float) * npx, out);
+}
+
+// Gaborish + EPF of a Modular-encoded frame (Frame.decodeFrame :457-461 with header.encoding == MODULAR): one sigma for the frame
+int32_t jxlb200_restore_uniform(jxlb200_ctx *ctx, const jxlb200_frame_params *p, float epf_sigma_for_modular,
+    const float *const in[3], float *const out[3]) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!p || !in || !out) return ctx->fail(JXLB200_E_ARG, "NULL pointer");
+    // a Modular frame has its own size, not a multiple of 8; sizes the tile kernel does not take go through the staged kernels
+    if (p->width <= 0 || p->height <= 0 || p->width > 65535 * 8 || p->height > 65535 * 8) return ctx->fail(JXLB200_E_ARG, "bad frame size");
+    if ((p->gab || p->epf_iters) && (p->width < 4 || p->height < 4))
+        return ctx->fail(JXLB200_E_UNSUPPORTED, "filters on a frame narrower than 4 pixels (mirrorCoordinate reflects more than once)");
+    if (p->epf_iters < 0 || p->epf_iters > 3) return ctx->fail(JXLB200_E_ARG, "epf_iters outside 0..3");
+    if (!(epf_sigma_for_modular == epf_sigma_for_modular)) return ctx->fail(JXLB200_E_ARG, "sigma is NaN");
+    int rc = 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = ((size_t)p->width * p->height + 3) & ~(size_t)3;      // planes stay 16-byte aligned
+    void *din[3];
+    CUDA_TRY(ctx, ctx->in_q.ensure(3 * sizeof(float) * npx));
+    for (int c = 0; c < 3; c++) {
+        if (!in[c] || !out[c]) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+        din[c] = ctx->in_q.as<float>() + c * npx;
+        CUDA_TRY(ctx, cudaMemcpyAsync(din[c], in[c], sizeof(float) * (size_t)p->width * p->height, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(ctx, ctx->out_planes.ensure(sizeof(float) * 3 * npx));
+    float *dout[3] = {ctx->out_planes.as<float>(), ctx->out_planes.as<float>() + npx, ctx->out_planes.as<float>() + 2 * npx};
+    if (!p->gab && p->epf_iters == 0 && p->color_mode == 0) {
+        for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(dout[c], din[c], sizeof(float) * npx, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        ctx->uniform_sigma = true;
+        ctx->uniform_inv_sigma = 1.0f / epf_sigma_for_modular;        // Frame.java:574
+        // hf_mul / sharpness are not read in this mode; any non-NULL pointers satisfy the argument checks below
+        rc = restore_dev(ctx, p, nullptr, (const float *const *)din, p->width, (const int32_t *)din[0], (const int32_t *)din[0], dout);
+        ctx->uniform_sigma = false;
+        if (rc) return rc;
+    }
+    return stage_out_planes(ctx, dout, sizeof(float) * (size_t)p->width * p->height, out);
 }
 
 int32_t jxlb200_gaborish(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const float *const in[3], float *const out[3]) {

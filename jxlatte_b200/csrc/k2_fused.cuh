@@ -271,7 +271,7 @@ static inline cudaError_t k2_fused_init_all() {
     return cudaSuccess;
 }
 // the fused kernel takes every frame that has at least one neighbourhood stage and is at least one reach tall / wide
-static inline bool k2_fused_supported(const K2Params &K) { return (K.gab || K.iters > 0) && K.rows >= 8 && K.W >= 8; }
+static inline bool k2_fused_supported(const K2Params &K) { return (K.gab || K.iters > 0) && K.rows >= 8 && K.W >= 8 && !(K.rows & 7) && !(K.W & 7); }
 
 template <int GAB, int ITERS> static void k2_fused_go(const K2Params &K, const float *inv_sigma, cudaStream_t st) {
     const dim3 grid((K.W + K2_TW - 1) / K2_TW, (K.rows + K2_TH - 1) / K2_TH);

@@ -37,6 +37,11 @@ __global__ void k2_sigma(const int32_t *__restrict__ hf_mul, const int32_t *__re
     }
 }
 
+// Modular-encoded frames have one sigma for the whole frame: invModularSigma = 1f / epfSigmaForModular (Frame.java:573-575, 604-607)
+__global__ void k2_sigma_fill(float v, long long first, long long n, float *__restrict__ inv_sigma) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) inv_sigma[first + i] = v;
+}
+
 // Rows [r0, r1) of the slab (may extend into halo rows).
 __global__ void k2_gab(K2Params P, const float *const in0, const float *const in1, const float *const in2,
                        float *out0, float *out1, float *out2, long long in_pitch, long long out_pitch, int r0, int r1) {

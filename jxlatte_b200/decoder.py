@@ -75,7 +75,8 @@ class CudaEngine:
         if st["qm_weights"] is not self._uploaded:      # same table object as the previous frame: already on the device
             self.rec.setWeights(st["qm_weights"], st["qm_offsets"])
             self._uploaded = st["qm_weights"]
-        if not (self.tolerance_mode and self.allow_tolerance_mode):
+        # the tolerance kernel is faster only with fewer than three EPF passes (profiles/r2_exact_vs_fast.md)
+        if not (self.tolerance_mode and self.allow_tolerance_mode and p.epf_iters < 3 and (p.gab or p.epf_iters)):
             return self.rec.reconstruct(p, st)
         from . import _lib
         self.rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_FUSED)
@@ -89,6 +90,9 @@ class CudaEngine:
 
     def color(self, p, planes):
         return self.rec.performColorTransforms(p, planes)
+
+    def restore_modular(self, p, planes, sigma):
+        return self.rec.restoreModularFrame(p, planes, sigma)
 
     def blend(self, op, canvas, a, b, fa, ra):
         self.rec.blend(op, canvas, a, b, fa, ra)
@@ -362,8 +366,6 @@ class JXLDecoder:
         else:
             if f["do_ycbcr"]:
                 raise NotImplementedError("YCbCr Modular frames")
-            if f["gab"] or f["epf_iters"] > 0:
-                raise NotImplementedError("Gaborish / EPF on Modular frames (constant-sigma EPF, frame sizes that are not multiples of 8)")
             if info["xyb_encoded"]:
                 # lossy Modular: channels are Y, X, B - Y in integers; Frame.decodeFrame :429-447 scales them by LFGlobal.lfDequant
                 # (X, Y, B order) into float XYB planes, which then take the same colour transform as VarDCT frames
@@ -378,9 +380,31 @@ class JXLDecoder:
                 ncol = info["color_channels"]
                 bufs = [_Buf(np.ascontiguousarray(mod[c][:h, :w])) for c in range(ncol)]          # int32 samples (Frame.java:452-455)
                 first = ncol
+            if f["gab"] or f["epf_iters"] > 0:
+                bufs = self._restore_modular(info, f, bufs, first, h, w)
         for e in range(len(info["extra_channels"])):
             bufs.append(_Buf(np.ascontiguousarray(mod[first + e][:h, :w])))
         return bufs, pending, p
+
+    def _restore_modular(self, info, f, bufs, ncol, h, w):
+        """Frame.decodeFrame :457-461 on a Modular-encoded frame: Gaborish and the edge-preserving filter cast the colour buffers
+        to float (castToFloat(bitsPerSample)) and run at the frame's own size with ONE sigma, 1f / epfSigmaForModular
+        (Frame.java:573-575, 604-607).  A one-colour frame filters channel 0 with the three distance terms all taken on that
+        channel (`colors == 1 ? 0 : c`, :642, 661): three copies of the plane through the same kernels, channel 0 kept."""
+        for c in range(ncol):
+            bufs[c].cast_to_float(info["bits_per_sample"])
+        p = self.frame_params(info, dict(f, padded_width=w, padded_height=h, global_scale=1))
+        p.color_mode = 0
+        if ncol == 1:
+            for c in (1, 2):
+                p.gab_w1[c], p.gab_w2[c] = p.gab_w1[0], p.gab_w2[0]
+            planes = [bufs[0].a, bufs[0].a, bufs[0].a]
+        else:
+            planes = [bufs[c].a for c in range(3)]
+        out = self.engine.restore_modular(p, planes, f["epf_sigma_for_modular"])
+        for c in range(ncol):
+            bufs[c] = _Buf(np.ascontiguousarray(out[c]))
+        return bufs
 
     # ---- JXLCodestreamDecoder.blendBuffers (:415-497) ----
     def _blend_buffers(self, info, canvas, frame_bufs, ref_bufs, patch_start, frame_offset, ref_offset, size, idx, frame_colors, binfo, patch):

@@ -206,6 +206,16 @@ class Reconstructor:
             raise ValueError("hf_mul / sharpness must have shape %s" % (shp,))
         return self._stage(self._L.jxlb200_epf, p, planes_in, _ptr(hm), _ptr(sh))
 
+    def restoreModularFrame(self, p, planes_in, epf_sigma_for_modular):
+        """Gaborish + EPF (+ p.color_mode) of a Modular-encoded frame: one sigma for the frame (jxlb200_restore_uniform)."""
+        inp = [_c(planes_in[c], np.float32) for c in range(3)]
+        if inp[0].shape != (p.height, p.width):
+            raise ValueError("planes have shape %s, expected %s" % (inp[0].shape, (p.height, p.width)))
+        out = np.empty((3, p.height, p.width), np.float32)
+        self._check(self._L.jxlb200_restore_uniform(self._h, C.byref(p), C.c_float(float(epf_sigma_for_modular)),
+                                                    _lib.planes([_ptr(a) for a in inp]), _lib.planes([_ptr(out[c]) for c in range(3)])))
+        return out
+
     def performColorTransforms(self, p, planes_in):
         return self._stage(self._L.jxlb200_color_transform, p, planes_in)
 

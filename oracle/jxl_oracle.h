@@ -87,6 +87,8 @@ void orc_gab(const orc_frame_params *p, const float *const in[3], float *const o
 /* Frame.performEdgePreservingFilter (:544-636). buf[3] updated in place (ping-pong handled inside).
  * returns -2 on sharpness outside [0,7]. */
 int32_t orc_epf(const orc_frame_params *p, float *const buf[3], const int32_t *hf_mul, const int32_t *sharpness, int32_t nthreads);
+/* Modular-encoded frames: one sigma for the frame (Frame.java:573-575, 604-607) */
+int32_t orc_epf_uniform(const orc_frame_params *p, float *const buf[3], float epf_sigma_for_modular, int32_t nthreads);
 /* JXLCodestreamDecoder.performColorTransforms (J/JXLCodestreamDecoder.java:256-283) */
 void orc_color(const orc_frame_params *p, float *const buf[3], int32_t nthreads);
 

@@ -163,6 +163,19 @@ def epf(p, planes, hf_mul, sharpness, nthreads=1):
     return np.stack(buf)
 
 
+def epf_uniform(p, planes, sigma_for_modular, nthreads=1):
+    """performEdgePreservingFilter on a Modular-encoded frame: invModularSigma = 1f / epfSigmaForModular everywhere."""
+    L = lib()
+    p = as_params(p)
+    buf = [np.array(planes[c], dtype=np.float32, order="C", copy=True) for c in range(3)]
+    L.orc_epf_uniform.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int32]
+    L.orc_epf_uniform.restype = C.c_int32
+    rc = L.orc_epf_uniform(C.byref(p), _planes(buf, C.c_float), float(sigma_for_modular), int(nthreads))
+    if rc:
+        raise RuntimeError("orc_epf_uniform rc=%d" % rc)
+    return np.stack(buf)
+
+
 def color(p, planes, nthreads=1):
     L = lib()
     p = as_params(p)

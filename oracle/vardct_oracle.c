@@ -1056,9 +1056,9 @@ static float epf_weight(const orc_frame_params *p, float sigmaScale, float dista
     return v < 0.0f ? 0.0f : v;
 }
 
+static int32_t epf_core(const orc_frame_params *p, float *const buf[3], float *inverseSigma, int32_t nthreads);
+
 int32_t orc_epf(const orc_frame_params *p, float *const buf[3], const int32_t *hf_mul, const int32_t *sharpness, int32_t nthreads) {
-    const float SQRT_H = (float)sqrt(0.5);
-    float stepMultiplier = 1.65f * 4.0f * (1.0f - SQRT_H);
     const int H = p->height, W = p->width;
     int blockHeight = (H + 7) >> 3;
     int blockWidth = (W + 7) >> 3;
@@ -1073,6 +1073,26 @@ int32_t orc_epf(const orc_frame_params *p, float *const buf[3], const int32_t *h
             inverseSigma[y * blockWidth + x] = 1.0f / sigma;
         }
     }
+    return epf_core(p, buf, inverseSigma, nthreads);
+}
+
+/* Modular-encoded frames: invModularSigma = 1f / header.restorationFilter.epfSigmaForModular for every pixel (Frame.java:573-575,
+ * 604-607).  A one-colour frame (`colors == 1 ? 0 : c`, :642, 661) is this function on three copies of the channel. */
+int32_t orc_epf_uniform(const orc_frame_params *p, float *const buf[3], float epf_sigma_for_modular, int32_t nthreads) {
+    const int H = p->height, W = p->width;
+    const size_t nb = (size_t)((H + 7) >> 3) * ((W + 7) >> 3);
+    float *inverseSigma = (float *)malloc(sizeof(float) * nb);
+    const float inv = 1.0f / epf_sigma_for_modular;
+    for (size_t i = 0; i < nb; i++) inverseSigma[i] = inv;
+    return epf_core(p, buf, inverseSigma, nthreads);
+}
+
+/* takes ownership of inverseSigma */
+static int32_t epf_core(const orc_frame_params *p, float *const buf[3], float *inverseSigma, int32_t nthreads) {
+    const float SQRT_H = (float)sqrt(0.5);
+    float stepMultiplier = 1.65f * 4.0f * (1.0f - SQRT_H);
+    const int H = p->height, W = p->width;
+    int blockWidth = (W + 7) >> 3;
     float *bufA[3], *bufB[3];
     for (int c = 0; c < 3; c++) {
         bufA[c] = buf[c];

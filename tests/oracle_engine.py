@@ -47,6 +47,14 @@ class OracleEngine:
     def modular(self, channels, transforms, bit_depth):
         return host.ModularTransforms(_OracleModularOps(), bit_depth).applyTransforms(channels, transforms)
 
+    def restore_modular(self, p, planes, sigma):
+        x = np.stack([np.asarray(pl, np.float32) for pl in planes])
+        if p.gab:
+            x = orc.gab(p, x, nthreads=self.nthreads)
+        if p.epf_iters:
+            x = orc.epf_uniform(p, x, sigma, nthreads=self.nthreads)
+        return x
+
     def color(self, p, planes):
         return orc.color(p, planes, nthreads=self.nthreads)
 

@@ -438,3 +438,71 @@ def test_tolerance_mode_for_8_bit_png_output(name):
     assert not np.array_equal(fast.planes, exact.planes)          # it really took the other kernel
     for opts in (JXLOptions(JXLOptions.OUTPUT_PNG, 16), JXLOptions(JXLOptions.OUTPUT_PFM), JXLOptions()):
         assert np.array_equal(JXLDecoder(path, options=opts).decode().planes, exact.planes)
+
+
+def _fake_modular_frame(real_info, chans, w, h, gab, iters, sigma, xyb, ncolor):
+    import copy
+    info = copy.deepcopy(real_info)
+    f = copy.deepcopy(info["frames"][0])
+    f.update(type=0, lf_level=0, encoding=1, width=w, height=h, padded_width=w, padded_height=h, gab=gab, epf_iters=iters,
+             epf_sigma_for_modular=sigma, lf_dequant=[1.0 / 4096] * 3, flags=0, is_last=True, save_as_reference=0, num_groups=1,
+             upsampling=1, do_ycbcr=False,
+             modular=dict(nb_meta=0, transformed=False, channels=[dict(h=h, w=w, hshift=0, vshift=0)] * len(chans), transforms=[]))
+    info["frames"] = [f]
+    info.update(width=w, height=h, xyb_encoded=xyb, color_channels=ncolor, bits_per_sample=8, orientation=1)
+    return _FakeParsed(info, {}, {0: list(chans)})
+
+
+@pytest.mark.parametrize("cfg", [dict(w=67, h=45, gab=True, iters=2, ncolor=3), dict(w=40, h=33, gab=True, iters=3, ncolor=1),
+                                 dict(w=64, h=48, gab=False, iters=1, ncolor=3)])
+def test_modular_frame_with_gaborish_and_epf_oracle(monkeypatch, orc, cfg):
+    """Gaborish / EPF on a Modular-encoded frame occur in no sample: fabricate one -- integer RGB (or grey)
+    channels, frame size not a multiple of 8 -- and hold the decoder to the stages written out by hand from Frame.java:505-679:
+    cast to float, Gaborish, EPF with invModularSigma = 1 / epfSigmaForModular, channel 0 for every distance term when grey."""
+    from oracle_engine import OracleEngine
+    from jxlatte_b200 import decoder as dec_mod
+    real = frontend.parse_file(os.path.join(S, "lenna.jxl"))
+    rng = np.random.default_rng(cfg["w"])
+    w, h, nc = cfg["w"], cfg["h"], cfg["ncolor"]
+    base = rng.integers(90, 160, size=(nc, h, w)) + (rng.random((nc, h, w)) < 0.02) * 60
+    chans = [np.ascontiguousarray(base[c], np.int32) for c in range(nc)]
+    sigma = 1.75
+    fake = _fake_modular_frame(real.info, chans, w, h, cfg["gab"], cfg["iters"], sigma, False, nc)
+    monkeypatch.setattr(dec_mod.frontend, "parse", lambda data, flags=0, strict=True: fake)
+    dec = JXLDecoder(b"unused", engine=OracleEngine())
+    got = dec.decode().planes
+    # by hand
+    p = dec.frame_params(fake.info, dict(fake.info["frames"][0]))
+    p.color_mode = 0
+    fl = [(chans[c].astype(np.float32) * (np.float32(1.0) / np.float32(255))) for c in range(nc)]
+    if nc == 1:
+        for c in (1, 2):
+            p.gab_w1[c], p.gab_w2[c] = p.gab_w1[0], p.gab_w2[0]
+        fl = [fl[0]] * 3
+    x = np.stack(fl)
+    if cfg["gab"]:
+        x = orc.gab(p, x)
+    x = orc.epf_uniform(p, x, sigma)
+    assert got.shape == (nc, h, w)
+    assert np.array_equal(got, x[:nc])
+    assert not np.array_equal(got, np.stack(fl)[:nc])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(w=67, h=45, gab=True, iters=2), dict(w=40, h=33, gab=True, iters=3), dict(w=264, h=136, gab=True, iters=3),
+                                 dict(w=64, h=48, gab=False, iters=1), dict(w=9, h=5, gab=True, iters=0)])
+def test_modular_frame_filters_kernel_matches_oracle(recon, orc, cfg):
+    """jxlb200_restore_uniform (one sigma for the frame; sizes that are not multiples of 8 take the staged kernels, the others the
+    fused tile kernel) == Gaborish + EPF of the oracle, bit for bit; sigma below 0.3 copies through like the reference."""
+    from jxlatte_b200 import default_frame_params
+    w, h = cfg["w"], cfg["h"]
+    p = default_frame_params(((w + 7) // 8) * 8, ((h + 7) // 8) * 8, epf_iters=cfg["iters"], gab=cfg["gab"], color_mode=0)
+    p.width, p.height = w, h
+    rng = np.random.default_rng(w * 7 + h)
+    planes = (rng.random((3, h, w), dtype=np.float32) * np.float32(0.3) + np.float32(0.3))
+    for sigma in (1.5, 0.2):
+        want = orc.gab(p, planes) if cfg["gab"] else planes
+        if cfg["iters"]:
+            want = orc.epf_uniform(p, want, sigma)
+        got = recon.restoreModularFrame(p, planes, sigma)
+        assert np.array_equal(got, want), "sigma %g: max abs err %g" % (sigma, np.abs(got - want).max())

@@ -140,6 +140,12 @@ def workload_config(args, iters):
             "l2": "inputs per step exceed the 126 MB L2 (no flush needed)"}
 
 
+def note(msg):
+    """progress on stderr (the JSON line alone goes to stdout)"""
+    sys.stderr.write("[bench %s r%s] %s\n" % (time.strftime("%H:%M:%S"), os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 class Workload:
     """One workload's device-resident inputs and its step (one pass of the hot path over one batch)."""
 
@@ -248,8 +254,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("building the %s workload" % args.workload)
     wl = Workload(args.workload, rec, dev, rank, world)
     W, H, iters, p, st = wl.W, wl.H, wl.iters, wl.p, wl.st
+    note("timing %d steps" % args.steps)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         wl.step()
@@ -266,6 +274,7 @@ def run_ours(args):
     # ---- stage timing for the roofline of the dominant kernel (rank 0, same process, CUDA events on the same stream) ----
     roof = None
     cpu = None
+    note("%.3f ms per step; stage timings" % (ms_max / args.steps))
     if rank == 0 and wl.halo is None:
         d = wl.first
         plane = torch.empty((3, H, W), dtype=torch.float32, device=dev)
@@ -332,6 +341,7 @@ def run_ours(args):
     # ---- e2e: the host-buffer C-ABI call a reference-side shim makes; pinned host memory, H2D + D2H inside.  EVERY rank
     # runs it at the same time (each on its own GPU and PCIe link); the aggregate is what N GPUs deliver to N callers ----
     e2e = None
+    note("e2e")
     if wl.halo is None and args.workload == "8k":
         keys = ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")
         hst = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in keys}
@@ -407,6 +417,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         for name in names:
             try:
+                note("sub-record " + name)
                 w2 = Workload(name, rec, dev, rank, world)
                 k = max(3, min(args.steps, 10))
                 ms2, _ = timed_steps(w2, stream, k, 3, barrier, dev, world)
@@ -447,6 +458,7 @@ def run_ours(args):
         except Exception as e:          # never let the side measurement break the bench line
             front = {"error": repr(e)}
 
+    note("done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True,

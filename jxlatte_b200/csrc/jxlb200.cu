@@ -634,6 +634,25 @@ int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
 
+// diagnostic: the shared-reciprocal divide of k2_exact against __fdiv_rn on n operand pairs drawn like the kernel's (divisor 1..13,
+// numerators image-like and arbitrary bit patterns); *mismatches must come back 0
+int32_t jxlb200_selftest_divide(jxlb200_ctx *ctx, int64_t n, int32_t seed, int64_t *mismatches) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!mismatches || n < 1) return ctx->fail(JXLB200_E_ARG, "bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr, h = 0;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(h)));
+    cudaMemsetAsync(d, 0, sizeof(h), ctx->stream);
+    kx_selftest_div<<<ctx->sms * 8, 256, 0, ctx->stream>>>((unsigned long long)n, (unsigned)seed, d);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return ctx->fail(JXLB200_E_CUDA, "selftest", e);
+    *mismatches = (int64_t)h;
+    return 0;
+}
+
 int32_t jxlb200_qm_default_params(jxlb200_qm_params out[17]) {
     if (!out) return JXLB200_E_ARG;
     qm::default_params(out);

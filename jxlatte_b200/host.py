@@ -135,6 +135,12 @@ class Reconstructor:
     def launch_count(self):
         return int(self._L.jxlb200_launch_count(self._h))
 
+    def selftest_divide(self, n, seed=1):
+        """Mismatches between stage 2's shared-reciprocal divide and __fdiv_rn on n operand pairs (must be 0)."""
+        bad = C.c_int64(-1)
+        self._check(self._L.jxlb200_selftest_divide(self._h, int(n), int(seed), C.byref(bad)))
+        return int(bad.value)
+
     def set_option(self, option, value):
         self._check(self._L.jxlb200_set_option(self._h, int(option), int(value)))
 

@@ -312,3 +312,12 @@ def test_packed_output_matches_oracle_pack(recon, orc, cfg):
     assert np.array_equal(recon.reconstruct_packed(p, st, bits=cfg["bits"], linear=False, crop=(cw, ch)), want2)
     with pytest.raises(ValueError):
         recon.reconstruct_packed(p, st, bits=12)
+
+
+@pytest.mark.gpu
+def test_shared_reciprocal_divide(recon):
+    """k2_exact divides a pixel's three channel sums by one sum of weights with a reciprocal refined once (the fast path of
+    __fdiv_rn itself, shared): on 2^26 operand pairs per seed -- divisors 1..13, numerators image-like, tiny, huge, zero, denormal
+    bit patterns -- every result must equal __fdiv_rn's bit for bit."""
+    for seed in (1, 2, 3):
+        assert recon.selftest_divide(1 << 26, seed) == 0

@@ -182,7 +182,7 @@ def _smooth_field(hb, wb, rng, coarse=16):
 
 def make_state(width, height, seed=SEED_BASE, mix="mixed", aligned=True, density=(0.30, 0.45, 0.25),
                decay=(7.0, 4.0, 8.0), amplitude=(0.004, 0.03, 0.03), sharp_zero_fraction=0.0,
-               params=None, qm_weights=None, qm_offsets=None):
+               params=None, qm_weights=None, qm_offsets=None, survey_spec=False):
     """Synthetic frame state.  width/height: padded size (multiples of 8).  Returns a dict of numpy arrays:
     qcoeff i32[3,H,W], lf f32[3,H/8,W/8], dct_select u8, block_origin u8, hf_mul i32, sharpness i32 (all [H/8,W/8]),
     x_from_y / b_from_y i32[ceil(H/64), ceil(W/64)].  Plane order is X, Y, B (Frame buffers, J/frame/Frame.java:42).
@@ -251,6 +251,17 @@ def make_state(width, height, seed=SEED_BASE, mix="mixed", aligned=True, density
         nz = rng.random((H, W), dtype=np.float32) < prob
         sign = rng.integers(0, 2, size=(H, W), dtype=np.int32) * 2 - 1
         qcoeff[c] = np.where(nz, mag * sign, 0)
+    if survey_spec:
+        # SURVEY.md 8(d) as written: 85 % zeros wherever the coefficient sits, else sign * (1 + Geometric(0.5)) clipped to +-63, and
+        # chroma-from-luma factors U{-32..32}.  Not image-like (|B| reaches several units) -- kept as the stress case for the sparse
+        # column walk of k1_big, reported beside the amplitude-aware default (profiles/r2_coefficient_density.md has real files).
+        for c in range(3):
+            mag = np.minimum(1 + rng.geometric(0.5, size=(H, W)).astype(np.int32), 63)
+            nz = rng.random((H, W), dtype=np.float32) < np.float32(0.15)
+            sign = rng.integers(0, 2, size=(H, W), dtype=np.int32) * 2 - 1
+            qcoeff[c] = np.where(nz, mag * sign, 0)
+        x_from_y = rng.integers(-32, 33, size=(th, tw), dtype=np.int32)
+        b_from_y = rng.integers(-32, 33, size=(th, tw), dtype=np.int32)
     st = dict(qcoeff=qcoeff, lf=lf, dct_select=ds, block_origin=origin, hf_mul=hf_mul, sharpness=sharp,
               x_from_y=x_from_y, b_from_y=b_from_y, width=W, height=H)
     if qm_weights is not None:

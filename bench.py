@@ -233,6 +233,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: native libraries (NCCL's version banner) write to file descriptor 1
+    # directly, so it points at stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -485,7 +490,10 @@ def run_ours(args):
             line["sub_records"] = sub
         if front:
             line["front_end"] = front
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     rec.close()
     if world > 1:
         dist.destroy_process_group()

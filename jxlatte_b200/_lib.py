@@ -78,6 +78,7 @@ SYMBOLS = {
     "jxlb200_noise": (_i32, [_vp, _P3, _i32, _i32, _i32, C.c_int64, _vp, C.c_float, C.c_float]),
     "jxlb200_splines": (_i32, [_vp, _P3, _i32, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, C.c_float]),
     "jxlb200_pack_samples": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "jxlb200_blend_batch": (_i32, [_vp, _i32, C.POINTER(_vp), _vp, _vp, _vp, _i32, _vp]),
     "jxlb200_blend": (_i32, [_vp, _vp, _i32, _i32, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64]),
 }
 
@@ -85,6 +86,10 @@ SYMBOLS = {
 class BlendOp(C.Structure):
     _fields_ = [("mode", C.c_int32), ("is_int", C.c_int32), ("is_alpha", C.c_int32), ("has_extra", C.c_int32),
                 ("clamp", C.c_int32), ("premult", C.c_int32)]
+
+class BlendItem(C.Structure):
+    _fields_ = [("op", BlendOp), ("h", C.c_int32), ("w", C.c_int32), ("plane", C.c_int32 * 5), ("y", C.c_int32 * 5), ("x", C.c_int32 * 5)]
+
 
 _LIB = None
 

@@ -1513,6 +1513,7 @@ int32_t jxlb200_blend(jxlb200_ctx *ctx, const jxlb200_blend_op *op, int32_t h, i
     BlendArgs A;
     A.mode = op->mode; A.is_int = op->is_int; A.is_alpha = op->is_alpha; A.has_extra = op->has_extra; A.clamp = op->clamp; A.premult = op->premult;
     A.h = h; A.w = w;
+    A.pa = A.pb = A.pfa = A.pra = A.pout = 0;
     A.a = base; A.b = base + sizeof(float) * n; A.fa = (const float *)(base + 2 * sizeof(float) * n);
     A.ra = (const float *)(base + 3 * sizeof(float) * n); A.out = base + 4 * sizeof(float) * n;
     CUDA_TRY(ctx, cudaMemcpy2DAsync((void *)A.a, row, frame, sizeof(float) * frame_pitch, row, h, cudaMemcpyHostToDevice, st));
@@ -1523,6 +1524,78 @@ int32_t jxlb200_blend(jxlb200_ctx *ctx, const jxlb200_blend_op *op, int32_t h, i
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpy2DAsync(canvas, sizeof(float) * canvas_pitch, A.out, row, row, h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+
+// ---- a frame's whole compositing in one call: the planes involved go to the device ONCE (only the rows any
+// rectangle touches), every rectangle of every channel is blended there in the order given -- later items see what earlier ones
+// wrote, as blendFrame / computePatches do (J/JXLCodestreamDecoder.java:212-254, 415-537) -- and the written planes come back once.
+// patches-lossless.jxl: ~2000 rectangles, two PCIe round trips instead of ~8000. ----
+int32_t jxlb200_blend_batch(jxlb200_ctx *ctx, int32_t n_planes, void *const planes[], const int32_t plane_h[], const int32_t plane_w[],
+    const int32_t writable[], int32_t n_items, const jxlb200_blend_item *items) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (n_planes < 1 || n_planes > 64 || !planes || !plane_h || !plane_w || !writable || n_items < 0 || (n_items > 0 && !items))
+        return ctx->fail(JXLB200_E_ARG, "bad arguments");
+    if (n_items == 0) return 0;
+    std::vector<int> lo(n_planes, 1 << 30), hi(n_planes, -1);
+    for (int k = 0; k < n_items; k++) {
+        const jxlb200_blend_item &it = items[k];
+        if (it.op.mode < 1 || it.op.mode > 4) return ctx->fail(JXLB200_E_STREAM, "Illegal blend mode");
+        if (it.h < 1 || it.w < 1) return ctx->fail(JXLB200_E_ARG, "empty blend rectangle");
+        int mode = it.op.mode;
+        if ((mode == 2 || mode == 3) && !it.op.has_extra) mode = 1;
+        if (it.op.is_int && mode != 1) return ctx->fail(JXLB200_E_ARG, "integer samples only blend with ADD (the reference casts to float first)");
+        const bool need_fa = (mode == 2 && !it.op.is_alpha) || mode == 3, need_ra = mode == 2 && !it.op.is_alpha;
+        for (int r = 0; r < 5; r++) {
+            const bool needed = r < 3 || (r == 3 && need_fa) || (r == 4 && need_ra);
+            const int pl = it.plane[r];
+            if (!needed) continue;
+            if (pl < 0 || pl >= n_planes || !planes[pl]) return ctx->fail(JXLB200_E_ARG, "blend item names a plane that was not given");
+            if (it.y[r] < 0 || it.x[r] < 0 || it.y[r] + it.h > plane_h[pl] || it.x[r] + it.w > plane_w[pl])
+                return ctx->fail(JXLB200_E_STREAM, "blend rectangle outside its buffer");
+            lo[pl] = std::min(lo[pl], it.y[r]); hi[pl] = std::max(hi[pl], it.y[r] + it.h);
+        }
+        if (!writable[it.plane[0]]) return ctx->fail(JXLB200_E_ARG, "blend item writes a plane not marked writable");
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<size_t> off(n_planes, 0);
+    size_t total = 0;
+    for (int pl = 0; pl < n_planes; pl++) {
+        if (hi[pl] < 0) continue;
+        off[pl] = total;
+        total += ((size_t)(hi[pl] - lo[pl]) * plane_w[pl] * 4 + 255) & ~(size_t)255;
+    }
+    CUDA_TRY(ctx, ctx->blend.ensure(total));
+    cudaStream_t st = ctx->stream;
+    char *base = (char *)ctx->blend.p;
+    for (int pl = 0; pl < n_planes; pl++)
+        if (hi[pl] >= 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(base + off[pl], (const char *)planes[pl] + (size_t)lo[pl] * plane_w[pl] * 4,
+                                          (size_t)(hi[pl] - lo[pl]) * plane_w[pl] * 4, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < n_items; k++) {
+        const jxlb200_blend_item &it = items[k];
+        BlendArgs A;
+        A.mode = it.op.mode; A.is_int = it.op.is_int; A.is_alpha = it.op.is_alpha; A.has_extra = it.op.has_extra; A.clamp = it.op.clamp; A.premult = it.op.premult;
+        A.h = it.h; A.w = it.w;
+        auto at = [&](int r) -> char * {
+            const int pl = it.plane[r];
+            if (pl < 0 || pl >= n_planes || hi[pl] < 0) return nullptr;
+            return base + off[pl] + ((size_t)(it.y[r] - lo[pl]) * plane_w[pl] + it.x[r]) * 4;
+        };
+        auto pitch = [&](int r) -> long long { const int pl = it.plane[r]; return (pl < 0 || pl >= n_planes) ? 1 : plane_w[pl]; };
+        A.out = at(0); A.a = at(1); A.b = at(2); A.fa = (const float *)at(3); A.ra = (const float *)at(4);
+        A.pout = pitch(0); A.pa = pitch(1); A.pb = pitch(2); A.pfa = pitch(3); A.pra = pitch(4);
+        const long long n = (long long)it.h * it.w;
+        k7_blend<<<(int)std::min<long long>(ctx->sms * 8, (n + 255) / 256), 256, 0, st>>>(A);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    for (int pl = 0; pl < n_planes; pl++)
+        if (hi[pl] >= 0 && writable[pl])
+            CUDA_TRY(ctx, cudaMemcpyAsync((char *)planes[pl] + (size_t)lo[pl] * plane_w[pl] * 4, base + off[pl],
+                                          (size_t)(hi[pl] - lo[pl]) * plane_w[pl] * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return 0;
 }

@@ -27,6 +27,35 @@ FLAG_NOISE, FLAG_PATCHES, FLAG_SPLINES, FLAG_USE_LF_FRAME = 1, 2, 16, 32
 TF_SRGB, TF_LINEAR = (1 << 24) + 13, (1 << 24) + 8
 
 
+def locate_view(v):
+    """A rectangle view of a channel buffer -> (a 2-D C-contiguous plane it is a window of, y, x), or None when it is not such a
+    window (the rectangle then takes the immediate blend call).  numpy collapses view chains onto the owning array, so the plane is
+    the owner seen as rows of the view's own row pitch: a [C, H, W] owner becomes one plane of C * H rows."""
+    if not isinstance(v, np.ndarray) or v.ndim != 2 or v.itemsize != 4:
+        return None
+    base = v
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    if base.itemsize != 4 or not base.flags["C_CONTIGUOUS"] or base.ndim < 1:
+        return None
+    if v.shape[1] > 1 and v.strides[1] != 4:
+        return None
+    if v.shape[0] > 1:
+        if v.strides[0] <= 0 or v.strides[0] % 4:
+            return None
+        W = v.strides[0] // 4
+    else:
+        W = base.shape[-1]
+    off = v.ctypes.data - base.ctypes.data
+    if off < 0 or off % 4 or W < 1 or base.size % W:
+        return None
+    y, x = divmod(off // 4, W)
+    plane = base.reshape(-1, W)
+    if y + v.shape[0] > plane.shape[0] or x + v.shape[1] > W:
+        return None
+    return plane, y, x
+
+
 class JXLOptions:
     """The reference's JXLOptions (J/JXLOptions.java:7-50), the fields that reach the reconstruction path."""
     OUTPUT_DEFAULT, OUTPUT_PNG, OUTPUT_PFM = -1, 0, 1
@@ -59,6 +88,8 @@ class CudaEngine:
         self._uploaded = None
         self.allow_tolerance_mode = allow_tolerance_mode
         self.tolerance_mode = False         # set per image by JXLDecoder from JXLOptions
+        self.batch_blends = True
+        self._batch_planes, self._batch_writable, self._batch_items, self._batch_index = [], [], [], {}
 
     def qm_default(self):
         if self._qm_default is None:        # HFGlobal.defaultParams tables: built once, shared by every frame that uses them
@@ -94,7 +125,40 @@ class CudaEngine:
     def restore_modular(self, p, planes, sigma):
         return self.rec.restoreModularFrame(p, planes, sigma)
 
+    # ---- compositing: the blends of a frame are queued and run in ONE device call (jxlb200_blend_batch) ----
+    def _locate(self, v):
+        loc = locate_view(v)
+        if loc is None:
+            return None
+        plane, y, x = loc
+        key = plane.ctypes.data
+        if key not in self._batch_index:
+            self._batch_index[key] = len(self._batch_planes)
+            self._batch_planes.append(plane)
+            self._batch_writable.append(False)
+        return self._batch_index[key], y, x
+
     def blend(self, op, canvas, a, b, fa, ra):
+        if self.batch_blends:
+            refs = [self._locate(v) if v is not None else None for v in (canvas, a, b, fa, ra)]
+            if refs[0] is not None and refs[1] is not None and refs[2] is not None and (fa is None or refs[3] is not None) and (ra is None or refs[4] is not None):
+                self._batch_writable[refs[0][0]] = True
+                self._batch_items.append((dict(op), canvas.shape, refs))
+                return
+            self.flush_blends()
+        self._blend_now(op, canvas, a, b, fa, ra)
+
+    def flush_blends(self):
+        """Run the queued rectangles (in order) and bring the written planes back.  Called before anything else touches the
+        buffers: a cast, a plain copy, the end of a frame's patches or of its blend."""
+        if self._batch_items:
+            planes, wr, items = self._batch_planes, self._batch_writable, self._batch_items
+            self._batch_planes, self._batch_writable, self._batch_items, self._batch_index = [], [], [], {}
+            self.rec.blend_batch(planes, wr, items)
+        else:
+            self._batch_planes, self._batch_writable, self._batch_index = [], [], {}
+
+    def _blend_now(self, op, canvas, a, b, fa, ra):
         self.rec.blend(op, canvas, a, b, fa, ra)
 
     def upsample(self, plane, k, weights):
@@ -157,8 +221,11 @@ class _Buf:
     def is_int(self):
         return self.a.dtype != np.float32
 
+    before_mutation = staticmethod(lambda: None)     # set by the decoder: queued device blends must land before a buffer changes
+
     def cast_to_float(self, depth):
         if self.is_int:
+            _Buf.before_mutation()
             scale = np.float32(1.0) / np.float32((1 << depth) - 1)
             self.a = self.a.astype(np.float32) * scale
 
@@ -429,6 +496,7 @@ class JXLDecoder:
             frame_buf.cast_to_float(depth)
             canvas.cast_to_float(depth)
         if mode == 0 or (ref_bufs is None and mode == 1):
+            self._flush_blends()
             rect(canvas, patch_start)[...] = rect(frame_buf, frame_offset)
             return
         if ref_bufs is None:
@@ -463,6 +531,7 @@ class JXLDecoder:
                 mode -= 1
         old_buf, new_buf = (ref_buf, frame_buf) if below else (frame_buf, ref_buf)     # passed as the Java's `frame`, `ref`
         if mode == 3 and has_extra and is_alpha:
+            self._flush_blends()
             rect(canvas, patch_start)[...] = rect(new_buf, frame_offset)                # copyToCanvas(..., ref), :389-391
             return
         if mode < 1 or mode > 4:
@@ -476,8 +545,19 @@ class JXLDecoder:
         self.engine.blend(op, rect(canvas, patch_start), rect(old_buf, frame_offset), rect(new_buf, ref_offset),
                           rect(frame_alpha, frame_offset) if need_fa else None, rect(ref_alpha, ref_offset) if need_ra else None)
 
+    def _flush_blends(self):
+        fl = getattr(self.engine, "flush_blends", None)
+        if fl is not None:
+            fl()
+
     # ---- JXLCodestreamDecoder.computePatches (:212-254) ----
     def _compute_patches(self, info, f, frame_bufs, frame_colors, reference):
+        try:
+            self._compute_patches_queued(info, f, frame_bufs, frame_colors, reference)
+        finally:
+            self._flush_blends()
+
+    def _compute_patches_queued(self, info, f, frame_bufs, frame_colors, reference):
         colors, nextra = info["color_channels"], len(info["extra_channels"])
         for patch in f["patches"]:
             if patch["ref"] > 3:
@@ -529,6 +609,7 @@ class JXLDecoder:
         if self.engine is None:
             self.engine = CudaEngine()
         info = parsed.info
+        _Buf.before_mutation = staticmethod(self._flush_blends)
         if hasattr(self.engine, "tolerance_mode"):
             self.engine.tolerance_mode = self.options.quantises_to_8_bits(info["bits_per_sample"])
         colors, nextra = info["color_channels"], len(info["extra_channels"])
@@ -617,6 +698,7 @@ class JXLDecoder:
                         else:
                             m, a, cl, src = f["blend_mode"], f["blend_alpha"], f["blend_clamp"], f["blend_source"]
                         self._blend_buffers(info, canvas[c], bufs, reference[src], ps, fo, ps, size, c, frame_colors, (m, a, bool(cl)), False)
+                    self._flush_blends()
             if save and not f["save_before_ct"]:
                 reference[f["save_as_reference"]] = canvas
             if f["is_last"] or f["duration"] != 0:

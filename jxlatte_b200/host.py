@@ -372,6 +372,30 @@ class Reconstructor:
         (cp, cpi), (ap, api), (bp, bpi), (fp, fpi), (rp, rpi) = rect(canvas), rect(a), rect(b), rect(fa), rect(ra)
         self._check(self._L.jxlb200_blend(self._h, C.byref(o), h, w, cp, cpi, ap, api, bp, bpi, fp, fpi, rp, rpi))
 
+    def blend_batch(self, planes, writable, items):
+        """A frame's whole compositing in one call (jxlb200_blend_batch).  planes: 2-D C-contiguous 4-byte numpy arrays (written in
+        place when writable[i]); items: (op dict, (h, w), [(plane index, y, x) or None] * 5) in the order canvas, `frame`, `ref`,
+        frame alpha, reference alpha -- blended on the device in that order, each seeing what the earlier ones wrote."""
+        n = len(planes)
+        for a in planes:
+            if a.ndim != 2 or a.itemsize != 4 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("blend planes must be 2-D C-contiguous arrays of 4-byte samples")
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in planes])
+        ph = np.array([a.shape[0] for a in planes], np.int32)
+        pw = np.array([a.shape[1] for a in planes], np.int32)
+        wr = np.array([1 if w else 0 for w in writable], np.int32)
+        arr = (_lib.BlendItem * len(items))()
+        for k, (op, (h, w), refs) in enumerate(items):
+            it = arr[k]
+            it.op = _lib.BlendOp(int(op["mode"]), int(op["is_int"]), int(op["is_alpha"]), int(op["has_extra"]), int(op["clamp"]), int(op["premult"]))
+            it.h, it.w = int(h), int(w)
+            for r in range(5):
+                if refs[r] is None:
+                    it.plane[r], it.y[r], it.x[r] = -1, 0, 0
+                else:
+                    it.plane[r], it.y[r], it.x[r] = int(refs[r][0]), int(refs[r][1]), int(refs[r][2])
+        self._check(self._L.jxlb200_blend_batch(self._h, n, ptrs, _ptr(ph), _ptr(pw), _ptr(wr), len(items), C.byref(arr) if len(items) else None))
+
     # -- Modular --
     def inverseRCT(self, channels, rct_type):
         """ModularStream.applyTransforms RCT branch: three equal-size channels, returns them as the reference leaves

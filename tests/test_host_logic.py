@@ -117,3 +117,21 @@ def test_narrow_coefficients_checks_the_range_and_keeps_int16_planes():
             narrow_coefficients(w)
     with pytest.raises(ValueError):
         narrow_coefficients([a.astype(np.float32) for a in q])
+
+
+def test_locate_view_finds_the_plane_of_a_blend_rectangle():
+    """The batched compositing call names rectangles as (plane, y, x): recovered from numpy views, through [C, H, W] owners too."""
+    import numpy as np
+    from jxlatte_b200.decoder import locate_view
+    a = np.arange(40 * 50, dtype=np.float32).reshape(40, 50)
+    pl, y, x = locate_view(a[7:19, 11:30])
+    assert pl.ctypes.data == a.ctypes.data and pl.shape == (40, 50) and (y, x) == (7, 11)
+    b = np.zeros((3, 16, 24), np.int32)
+    pl, y, x = locate_view(b[2][5:9, 3:20])
+    assert pl.ctypes.data == b.ctypes.data and pl.shape == (48, 24) and (y, x) == (32 + 5, 3)      # [C, H, W] owner = one tall plane
+    pl, y, x = locate_view(np.ascontiguousarray(b[1][:16, :24])[0:16, 0:24])     # already contiguous: still a view of b
+    assert pl.shape == (48, 24) and (y, x) == (16, 0)
+    assert locate_view(a[::2, :]) is None                 # rows skipped: not a window
+    assert locate_view(a[:, ::2]) is None
+    assert locate_view(a.astype(np.float64)[1:3, 1:3]) is None
+    assert locate_view(a.T[1:3, 1:3]) is None

@@ -131,7 +131,8 @@ def test_locate_view_finds_the_plane_of_a_blend_rectangle():
     assert pl.ctypes.data == b.ctypes.data and pl.shape == (48, 24) and (y, x) == (32 + 5, 3)      # [C, H, W] owner = one tall plane
     pl, y, x = locate_view(np.ascontiguousarray(b[1][:16, :24])[0:16, 0:24])     # already contiguous: still a view of b
     assert pl.shape == (48, 24) and (y, x) == (16, 0)
-    assert locate_view(a[::2, :]) is None                 # rows skipped: not a window
+    pl, y, x = locate_view(a[::2, :])                     # every other row IS a window: of the owner seen 100 samples wide
+    assert pl.shape == (20, 100) and (y, x) == (0, 0) and np.array_equal(pl[:, :50], a[::2, :])
     assert locate_view(a[:, ::2]) is None
     assert locate_view(a.astype(np.float64)[1:3, 1:3]) is None
     assert locate_view(a.T[1:3, 1:3]) is None

@@ -174,6 +174,35 @@ def test_blend_kernel_matches_oracle(recon):
         recon.blend(dict(op, mode=4), got, ia[:h, :w], ib[:h, :w])
 
 
+@pytest.mark.gpu
+def test_blend_batch_matches_sequential_oracle(recon):
+    """jxlb200_blend_batch: 300 overlapping rectangles over six planes (two written, canvas aliasing the `frame` operand as patches
+    do), blended on the device in order, == the oracle applying them one after the other on the host arrays."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(21)
+    H, W = 72, 90
+    planes = [rng.uniform(-0.2, 1.2, (H, W)).astype(np.float32) for _ in range(6)]
+    want = [p.copy() for p in planes]
+    got = [p.copy() for p in planes]
+    items = []
+    for k in range(300):
+        h, w = int(rng.integers(1, 30)), int(rng.integers(1, 40))
+        mode = int(rng.integers(1, 5))
+        is_alpha = int(rng.integers(0, 2)) if mode != 3 else 0
+        op = dict(mode=mode, is_int=0, is_alpha=is_alpha, has_extra=1, clamp=int(rng.integers(0, 2)), premult=int(rng.integers(0, 2)))
+        cv = int(rng.integers(0, 2))                       # planes 0 and 1 are canvases
+        pos = [(int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))) for _ in range(5)]
+        refs = [(cv, *pos[0]), (cv, *pos[0]) if k % 2 else (2, *pos[1]), (3, *pos[2]), (4, *pos[3]), (5, *pos[4])]
+        items.append((op, (h, w), refs))
+        v = [want[r[0]][r[1]:r[1] + h, r[2]:r[2] + w] for r in refs]
+        orc.blend(op, v[0], v[1], v[2], v[3], v[4])
+    recon.blend_batch(got, [True, True, False, False, False, False], items)
+    for i in range(6):
+        assert np.array_equal(got[i], want[i], equal_nan=True), "plane %d" % i
+    with pytest.raises(Exception):
+        recon.blend_batch(got, [False] * 6, items[:1])   # writes a plane not marked writable
+
+
 def test_mutated_inputs_never_crash():
     """Bit flips, truncations and overwritten runs: the C++ front end must come back with a status, not a crash or a hang
     (run under -fsanitize=address,undefined when the fixtures were made: clean)."""

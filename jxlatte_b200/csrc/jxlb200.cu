@@ -1165,12 +1165,18 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
     std::vector<int> slab_start;
     host_slab_schedule(H, slab_start);
     const int nslab = (int)slab_start.size();
-    std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab), ev_k1(nslab);
+    // JXLB200_TIMELINE=1: per-slab event times of this call on stderr (upload done | stage 1 done | stage 2 done | download done)
+    static const bool timeline = getenv("JXLB200_TIMELINE") != nullptr;
+    const unsigned evflag = timeline ? cudaEventDefault : cudaEventDisableTiming;
+    std::vector<cudaEvent_t> ev_up(nslab), ev_k2(nslab), ev_k1(nslab), ev_dn(timeline ? nslab : 0);
+    cudaEvent_t ev_t0 = nullptr;
     for (int i = 0; i < nslab; i++) {
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k1[i], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_up[i], evflag));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k2[i], evflag));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_k1[i], evflag));
+        if (timeline) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev_dn[i], evflag));
     }
+    if (timeline) { CUDA_TRY(ctx, cudaEventCreate(&ev_t0)); cudaEventRecord(ev_t0, up); }
     rc = 0;
     for (int i = 0; i < nslab && !rc; i++) {
         const int y0 = slab_start[i], y1 = i + 1 < nslab ? slab_start[i + 1] : H, rows = y1 - y0;
@@ -1206,9 +1212,9 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             jxlb200_slab sl = {a, r2, H, a > 0 ? 1 : 0, b < H ? 1 : 0};
             const float *m3[3] = {mid[0] + o2, mid[1] + o2, mid[2] + o2};
             float *o3[3] = {dout[0] + o2, dout[1] + o2, dout[2] + o2};
-            if (comp2 != comp) {
+            if (comp2 != comp || timeline) {
                 cudaEventRecord(ev_k1[i], comp);
-                cudaStreamWaitEvent(comp2, ev_k1[i], 0);
+                if (comp2 != comp) cudaStreamWaitEvent(comp2, ev_k1[i], 0);
             }
             ctx->stream = comp2;
             rc = restore_dev(ctx, &ps, nslab > 1 ? &sl : nullptr, m3, W, M.hf + (size_t)(a / 8) * wb, M.sharp + (size_t)(a / 8) * wb, o3);
@@ -1217,6 +1223,7 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             if (pk) {       // sRGB + quantise + interleave on the compute stream, then a quarter (or half) of the bytes go back
                 rc = send_packed(dout, a, b, comp2, down, ev_k2[i]);
                 if (rc) break;
+                if (timeline) cudaEventRecord(ev_dn[i], down);
                 continue;
             }
             cudaEventRecord(ev_k2[i], comp2);
@@ -1225,10 +1232,22 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
                 cudaError_t e = cudaMemcpyAsync(out[c] + o2, o3[c], sizeof(float) * (size_t)r2 * W, cudaMemcpyDeviceToHost, down);
                 if (e != cudaSuccess) rc = ctx->fail(JXLB200_E_CUDA, "cudaMemcpyAsync (download)", e);
             }
+            if (timeline) cudaEventRecord(ev_dn[i], down);
         }
     }
     cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(comp), e3 = cudaStreamSynchronize(down);
     if (comp2 != comp && e2 == cudaSuccess) e2 = cudaStreamSynchronize(comp2);
+    if (timeline && !rc && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        fprintf(stderr, "[jxlb200 timeline] %d slabs, %s coefficients, %s out (ms since the call's first upload)\n", nslab, narrow ? "int16" : "int32", pk ? "packed" : "float32");
+        for (int i = 0; i < nslab; i++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, ev_t0, ev_up[i]); cudaEventElapsedTime(&b, ev_t0, ev_k1[i]);
+            cudaEventElapsedTime(&c, ev_t0, ev_k2[i]); cudaEventElapsedTime(&d, ev_t0, ev_dn[i]);
+            fprintf(stderr, "[jxlb200 timeline] slab %2d rows %4d..%4d: uploaded %.3f  stage1 %.3f  stage2 %.3f  downloaded %.3f\n", i, slab_start[i],
+                    i + 1 < nslab ? slab_start[i + 1] : H, a, b, c, d);
+        }
+    }
+    if (timeline) { for (cudaEvent_t e : ev_dn) cudaEventDestroy(e); if (ev_t0) cudaEventDestroy(ev_t0); }
     for (int i = 0; i < nslab; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k2[i]); cudaEventDestroy(ev_k1[i]); }
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)

@@ -64,6 +64,8 @@ struct jxlb200_ctx {
     int opt_stage2 = 0;
     bool uniform_sigma = false;         // jxlb200_restore_uniform: one 1/sigma for every block instead of the hf_mul / sharpness maps
     float uniform_inv_sigma = 0.0f;
+    int opt_pipe_rows = 0;              // host entry points: rows per pipelined slab (0 = the measured default for the output format)
+    int opt_pipe_fanout = -1;           // stage 1 of a slab on six streams (1) or one (0); -1 = by slab height
     int opt_overlap_rows = JXLB200_OVERLAP_ROWS;   // device-resident whole path: slab height for overlapping stage 2 of slab j with stage 1 of slab j+2 (0 = off)
     std::vector<cudaEvent_t> ev_pool;
 
@@ -631,6 +633,8 @@ int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
         return 0;
     }
     if (option == JXLB200_OPT_OVERLAP_ROWS && value >= 0 && (value & 255) == 0) { ctx->opt_overlap_rows = value; return 0; }
+    if (option == JXLB200_OPT_PIPE_ROWS && value >= 0 && (value & 255) == 0) { ctx->opt_pipe_rows = value; return 0; }
+    if (option == JXLB200_OPT_PIPE_FANOUT && value >= -1 && value <= 1) { ctx->opt_pipe_fanout = value; return 0; }
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
 
@@ -996,15 +1000,18 @@ static int stage_out_planes(jxlb200_ctx *ctx, const float *const dev[3], size_t 
 // with has_top / has_bottom; the kernels only need a range to start on a block row).
 // Slab schedule of the pipelined host entry point: the first two and the last two slabs are one group row (256) each so
 // that the pipeline fills and drains quickly, the ones in between are JXLB200_PIPE_ROWS.
-static void host_slab_schedule(int H, std::vector<int> &slab_start);
+static void host_slab_schedule(int H, std::vector<int> &slab_start, int pipe_rows = 0);
 #ifndef JXLB200_HOST_TWO_COMPUTE_STREAMS
 #define JXLB200_HOST_TWO_COMPUTE_STREAMS 1   /* measured on B200, 8K frame, int32 / int16 coefficients: one compute stream 10.40 / 9.29 ms, two 10.31 / 9.21 ms (256-row slabs: 11.07 / 11.49 -> 10.53 / 10.39) */
+#endif
+#ifndef JXLB200_PIPE_ROWS_PACKED
+#define JXLB200_PIPE_ROWS_PACKED 1024   /* packed samples out: measured on B200 in profiles/r2_host_entry_packed.md */
 #endif
 #ifndef JXLB200_PIPE_ROWS
 #define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
 #endif
-static void host_slab_schedule(int H, std::vector<int> &slab_start) {
-    const int G = (H + 255) / 256, per = JXLB200_PIPE_ROWS / 256;     // group rows in the frame / per middle slab
+static void host_slab_schedule(int H, std::vector<int> &slab_start, int pipe_rows) {
+    const int G = (H + 255) / 256, per = (pipe_rows > 0 ? pipe_rows : JXLB200_PIPE_ROWS) / 256;     // group rows in the frame / per middle slab
     const int edge = G >= 4 + per ? 2 : (G >= 2 + per ? 1 : 0);        // single-group-row slabs at each end
     int g = 0;
     slab_start.clear();
@@ -1162,9 +1169,15 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
         for (int c = 0; c < 3; c++)      // the LF planes are 1/64 of the coefficients: whole, up front
             CUDA_TRY(ctx, cudaMemcpyAsync(dlf[c], lf[c], sizeof(float) * nb, cudaMemcpyHostToDevice, up));
     }
+    // Slab height.  Every slab costs stage 1 about 0.6 ms of launch latency whatever its size (a dozen persistent launches in a row:
+    // JXLB200_TIMELINE shows it), so 11 slabs of 512 rows make stage 1, not the bus, the limit of an 8K call as soon as the download is
+    // small.  With float32 planes going back (12 B/px down) the bus is the limit and short slabs keep it busy; with packed samples
+    // (3 or 6 B/px down) taller slabs win.
+    const int pipe_rows = ctx->opt_pipe_rows > 0 ? ctx->opt_pipe_rows : (pk ? JXLB200_PIPE_ROWS_PACKED : JXLB200_PIPE_ROWS);
     std::vector<int> slab_start;
-    host_slab_schedule(H, slab_start);
+    host_slab_schedule(H, slab_start, pipe_rows);
     const int nslab = (int)slab_start.size();
+    const bool s1_fanout = ctx->opt_pipe_fanout >= 0 ? ctx->opt_pipe_fanout != 0 : pipe_rows >= 1024;
     // JXLB200_TIMELINE=1: per-slab event times of this call on stderr (upload done | stage 1 done | stage 2 done | download done)
     static const bool timeline = getenv("JXLB200_TIMELINE") != nullptr;
     const unsigned evflag = timeline ? cudaEventDefault : cudaEventDisableTiming;
@@ -1199,7 +1212,7 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
             const float *l3[3] = {dlf[0] + (size_t)(y0 / 8) * wb, dlf[1] + (size_t)(y0 / 8) * wb, dlf[2] + (size_t)(y0 / 8) * wb};
             float *m3[3] = {mid[0] + off, mid[1] + off, mid[2] + off};
             rc = invert_dev(ctx, &ps, q3, l3, M.ds + (size_t)(y0 / 8) * wb, M.bo + (size_t)(y0 / 8) * wb, M.hf + (size_t)(y0 / 8) * wb,
-                            M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W, false);
+                            M.xfy + (size_t)(y0 / 64) * tw, M.bfy + (size_t)(y0 / 64) * tw, m3, W, s1_fanout);
             if (rc) break;
         }
         {   // stage 2 of the rows whose lower halo now exists: the slab shifted up by HALO rows

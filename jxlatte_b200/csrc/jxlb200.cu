@@ -1005,7 +1005,7 @@ static void host_slab_schedule(int H, std::vector<int> &slab_start, int pipe_row
 #define JXLB200_HOST_TWO_COMPUTE_STREAMS 1   /* measured on B200, 8K frame, int32 / int16 coefficients: one compute stream 10.40 / 9.29 ms, two 10.31 / 9.21 ms (256-row slabs: 11.07 / 11.49 -> 10.53 / 10.39) */
 #endif
 #ifndef JXLB200_PIPE_ROWS_PACKED
-#define JXLB200_PIPE_ROWS_PACKED 1024   /* packed samples out: measured on B200 in profiles/r2_host_entry_packed.md */
+#define JXLB200_PIPE_ROWS_PACKED 768   /* packed samples out: measured on B200, profiles/r2_host_entry_packed.md (512 / 768 / 1024 rows with the stage-1 fan-out: 5.70 / 5.53 / 5.64 ms) */
 #endif
 #ifndef JXLB200_PIPE_ROWS
 #define JXLB200_PIPE_ROWS 512   /* measured on B200, 8K frame: 256 rows 12.0 ms, 512 rows 11.2 ms, 1024 rows 12.7 ms; again with the 2.9 ms kernels: 256 / 512 / 768 rows 11.4 / 11.2 / 11.7 ms; PCIe floor (398 MB each way, duplex) 8.4 ms */
@@ -1177,7 +1177,9 @@ static int reconstruct_host(jxlb200_ctx *ctx, const jxlb200_frame_params *p, con
     std::vector<int> slab_start;
     host_slab_schedule(H, slab_start, pipe_rows);
     const int nslab = (int)slab_start.size();
-    const bool s1_fanout = ctx->opt_pipe_fanout >= 0 ? ctx->opt_pipe_fanout != 0 : pipe_rows >= 1024;
+    // stage 1 of a slab on six streams: a win whenever the bus is not the limit (int16 coefficients in or packed samples out: 9.19 ->
+    // 8.75 ms and 7.58 -> 5.70 ms per 8K frame), a small loss when it is (int32 in, float32 out: 10.28 -> 10.69 ms)
+    const bool s1_fanout = ctx->opt_pipe_fanout >= 0 ? ctx->opt_pipe_fanout != 0 : (narrow || pk != nullptr);
     // JXLB200_TIMELINE=1: per-slab event times of this call on stderr (upload done | stage 1 done | stage 2 done | download done)
     static const bool timeline = getenv("JXLB200_TIMELINE") != nullptr;
     const unsigned evflag = timeline ? cudaEventDefault : cudaEventDisableTiming;

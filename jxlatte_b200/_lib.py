@@ -79,6 +79,7 @@ SYMBOLS = {
     "jxlb200_noise": (_i32, [_vp, _P3, _i32, _i32, _i32, C.c_int64, _vp, C.c_float, C.c_float]),
     "jxlb200_splines": (_i32, [_vp, _P3, _i32, _i32, _i32, _vp, _vp, _vp, _i32, C.c_float, C.c_float]),
     "jxlb200_pack_samples": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "jxlb200_lf_dequant": (_i32, [_vp, _i32, _i32, _vp, C.c_float, C.c_float, _i32, _i32, _P3, _vp, _P3]),
     "jxlb200_blend_batch": (_i32, [_vp, _i32, C.POINTER(_vp), _vp, _vp, _vp, _i32, _vp]),
     "jxlb200_blend": (_i32, [_vp, _vp, _i32, _i32, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64]),
 }

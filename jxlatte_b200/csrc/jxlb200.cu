@@ -1731,6 +1731,40 @@ int32_t jxlb200_splines(jxlb200_ctx *ctx, float *const planes[3], int32_t h, int
 }
 
 
+// ---- LF coefficients on host planes (k8_lf_dequant): LFCoefficients' dequantisation + LF chroma-from-luma + adaptive smoothing ----
+int32_t jxlb200_lf_dequant(jxlb200_ctx *ctx, int32_t hb, int32_t wb, const float scaled_dequant[3], float k_x, float k_b,
+    int32_t cfl, int32_t adaptive_smoothing, const int32_t *const lf_quant[3], const uint8_t *extra_precision, float *const out[3]) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (hb < 1 || wb < 1 || !scaled_dequant || !lf_quant || !extra_precision || !out) return ctx->fail(JXLB200_E_ARG, "bad arguments");
+    for (int c = 0; c < 3; c++)
+        if (!lf_quant[c] || !out[c]) return ctx->fail(JXLB200_E_ARG, "NULL plane pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)hb * wb;
+    const int gcols = (wb + 255) >> 8, ng = gcols * ((hb + 255) >> 8);
+    for (int g = 0; g < ng; g++)
+        if (extra_precision[g] > 3) return ctx->fail(JXLB200_E_STREAM, "extraPrecision is a 2-bit field");
+    CUDA_TRY(ctx, ctx->blend.ensure(sizeof(float) * 6 * n + ng + 64));
+    LfArgs A;
+    cudaStream_t st = ctx->stream;
+    for (int c = 0; c < 3; c++) {
+        int32_t *dq = ctx->blend.as<int32_t>() + c * n;
+        A.q[c] = dq;
+        A.out[c] = ctx->blend.as<float>() + (3 + c) * n;
+        A.sd[c] = scaled_dequant[c];
+        CUDA_TRY(ctx, cudaMemcpyAsync(dq, lf_quant[c], sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    uint8_t *dep = ctx->blend.as<uint8_t>() + sizeof(float) * 6 * n;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dep, extra_precision, ng, cudaMemcpyHostToDevice, st));
+    A.ep = dep; A.hb = hb; A.wb = wb; A.gcols = gcols; A.cfl = cfl ? 1 : 0; A.smooth = adaptive_smoothing ? 1 : 0; A.kx = k_x; A.kb = k_b;
+    k8_lf_dequant<<<(int)std::min<size_t>((size_t)ctx->sms * 8, (n + 255) / 256), 256, 0, st>>>(A);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    for (int c = 0; c < 3; c++) CUDA_TRY(ctx, cudaMemcpyAsync(out[c], A.out[c], sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+
 // ---- PNG-ready samples from host planes (k8_pack_samples) ----
 int32_t jxlb200_pack_samples(jxlb200_ctx *ctx, const void *const planes[], const int32_t is_int[], const int32_t depth[],
     int32_t n_channels, int32_t n_color, int32_t linear, int32_t h, int32_t w, int32_t bits, uint8_t *out) {

@@ -125,6 +125,9 @@ class CudaEngine:
     def restore_modular(self, p, planes, sigma):
         return self.rec.restoreModularFrame(p, planes, sigma)
 
+    def lf_dequant(self, q, ep, scaled_dequant, kx, kb, smooth):
+        return self.rec.dequantLF(q, ep, scaled_dequant, kx, kb, cfl=True, smooth=smooth)
+
     # ---- compositing: the blends of a frame are queued and run in ONE device call (jxlb200_blend_batch) ----
     def _locate(self, v):
         loc = locate_view(v)
@@ -417,6 +420,13 @@ class JXLDecoder:
                         raise frontend.InvalidBitstreamError("LF frame smaller than the frame that uses it")
                     lf[c] = a
                 st["lf"] = lf
+            else:
+                # LFCoefficients' dequantisation + LF chroma-from-luma + adaptive smoothing on the device (jxlb200_lf_dequant) from the
+                # quantised LF the front end decoded; the front end's own host result (the same arithmetic in C++) is what the oracle
+                # engine keeps using, so the whole-file parity tests hold the two to each other bit for bit
+                lfq = parsed.lf_quantised(k) if hasattr(self.engine, "lf_dequant") and hasattr(parsed, "lf_quantised") else None
+                if lfq is not None:
+                    st["lf"] = self.engine.lf_dequant(*lfq)
             if f["type"] == 1:
                 p.color_mode = 0                      # LF frames are kept as they leave Frame.decodeFrame (no colour transform)
             # patches and saveBeforeCT act on the planes BEFORE the colour transform (JXLCodestreamDecoder.java:611-616)

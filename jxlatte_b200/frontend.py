@@ -123,6 +123,26 @@ class ParsedImage:
             st[k] = self.array(frame, k, 0, shp)
         return st
 
+    def lf_quantised(self, frame):
+        """The LF planes BEFORE LFCoefficients' arithmetic, for the device LF kernel (jxlb200_lf_dequant): (lf_quant int32 [3, H/8, W/8]
+        in X, Y, B order, extraPrecision per LF group, scaledDequant[3], kX, kB, adaptive smoothing?), or None when the frame takes its LF
+        from an LF frame or is chroma-subsampled (the front end's own planes are used then)."""
+        f = self.frames[frame]
+        if f["flags"] & 32 or any(f["shift_x"]) or any(f["shift_y"]):
+            return None
+        hb, wb = f["padded_height"] // 8, f["padded_width"] // 8
+        try:
+            q = np.stack([self.array(frame, "lf_quant", c, (hb, wb)) for c in range(3)])
+            ep = self.array(frame, "lf_extra_precision", 0)
+        except Exception:
+            return None
+        if ep.size != ((hb + 255) // 256) * ((wb + 255) // 256):
+            return None
+        f32 = np.float32
+        kx = f32(f["base_corr_x"]) + (f32(f["x_factor_lf"]) - f32(128.0)) / f32(f["color_factor"])     # LFCoefficients.java:81-82
+        kb = f32(f["base_corr_b"]) + (f32(f["b_factor_lf"]) - f32(128.0)) / f32(f["color_factor"])
+        return q, ep, [f32(v) for v in f["scaled_dequant"]], kx, kb, not bool(f["flags"] & 128)
+
     def modular_channels(self, frame):
         m = self.frames[frame]["modular"]
         return [self.array(frame, "modular", i, (c["h"], c["w"])) for i, c in enumerate(m["channels"])]

@@ -116,7 +116,7 @@ void describe(jxlf_image &im) {
         j.num("toc_bit_offset", (unsigned long long)f.toc_bit_offset); j.num("toc_first_section", (unsigned long long)f.toc_first_section);
         j.iarr("toc_lengths", f.toc_lengths.begin(), f.toc_lengths.end());
         j.num("num_groups", f.num_groups); j.num("num_lf_groups", f.num_lf_groups);
-        j.farr("lf_dequant", f.lf_dequant, f.lf_dequant + 3); j.num("global_scale", f.global_scale); j.num("quant_lf", f.quant_lf);
+        j.farr("lf_dequant", f.lf_dequant, f.lf_dequant + 3); j.farr("scaled_dequant", f.scaled_dequant, f.scaled_dequant + 3); j.num("global_scale", f.global_scale); j.num("quant_lf", f.quant_lf);
         j.num("color_factor", f.color_factor); j.flt("base_corr_x", f.base_corr_x); j.flt("base_corr_b", f.base_corr_b);
         j.num("x_factor_lf", f.x_factor_lf); j.num("b_factor_lf", f.b_factor_lf);
         j.farr("noise", f.noise, f.noise + 8); j.num("num_patches", f.num_patches); j.num("num_splines", f.num_splines);
@@ -254,6 +254,8 @@ int32_t jxlf_array(const jxlf_image *im, int32_t frame, const char *name, int32_
     auto give = [&](const auto &v, int dt) { *ptr = v.data(); *count = (int64_t)v.size(); *dtype = dt; return 0; };
     if (n == "qcoeff" && index >= 0 && index < 3) return give(f.qcoeff[index], 0);
     if (n == "lf" && index >= 0 && index < 3) return give(f.lf[index], 1);
+    if (n == "lf_quant" && index >= 0 && index < 3) return give(f.lf_quant[index], 0);
+    if (n == "lf_extra_precision") return give(f.lf_extra_precision, 2);
     if (n == "dct_select") return give(f.dct_select, 2);
     if (n == "block_origin") return give(f.block_origin, 2);
     if (n == "hf_mul") return give(f.hf_mul, 0);

@@ -59,6 +59,9 @@ struct FrameData {
     // VarDCT state, frame level
     std::vector<int32_t> qcoeff[3];
     std::vector<float> lf[3];
+    std::vector<int32_t> lf_quant[3];            // the same planes before LFCoefficients' arithmetic (X, Y, B order), for the device LF kernel
+    std::vector<uint8_t> lf_extra_precision;     // per LF group
+    float scaled_dequant[3] = {0, 0, 0};
     std::vector<uint8_t> dct_select, block_origin;
     std::vector<int32_t> hf_mul, sharpness, x_from_y, b_from_y;
     bool quant_all_default = true;
@@ -306,6 +309,7 @@ class FrameDecoder {
             f.global_scale = (int)br.u32(1, 11, 2049, 11, 4097, 12, 8193, 16);
             f.quant_lf = (int)br.u32(16, 0, 1, 5, 1, 8, 1, 16);
             for (int i = 0; i < 3; i++) scaled_dequant_[i] = (float)(1 << 16) * f.lf_dequant[i] / (float)(f.global_scale * f.quant_lf);
+            for (int i = 0; i < 3; i++) f.scaled_dequant[i] = scaled_dequant_[i];
             read_block_context(br);
             if (!br.flag()) {
                 f.color_factor = (int)br.u32(84, 0, 256, 0, 2, 8, 258, 16);
@@ -362,6 +366,7 @@ class FrameDecoder {
         for (int c = 0; c < 3; c++) {
             f.qcoeff[c].assign((size_t)(f.padded_h >> f.hdr.shift_y[c]) * (f.padded_w >> f.hdr.shift_x[c]), 0);
             f.lf[c].assign((size_t)(bh >> f.hdr.shift_y[c]) * (bw >> f.hdr.shift_x[c]), 0.0f);
+            f.lf_quant[c].assign((size_t)(bh >> f.hdr.shift_y[c]) * (bw >> f.hdr.shift_x[c]), 0);
         }
         f.dct_select.assign((size_t)bh * bw, 0);
         f.block_origin.assign((size_t)bh * bw, 0);
@@ -482,6 +487,8 @@ class FrameDecoder {
             info[kMap[i]] = Channel(ch_h[i], ch_w[i], h.shift_y[i], h.shift_x[i]);
         }
         const int extra_precision = (int)br.bits(2);
+        if (f.lf_extra_precision.size() != (size_t)f.num_lf_groups) f.lf_extra_precision.assign(f.num_lf_groups, 0);
+        f.lf_extra_precision[g] = (uint8_t)extra_precision;
         ModularStream ms;
         ms.init(br, fc_, 1 + g, std::move(info));
         ms.decode_channels(br);
@@ -508,8 +515,11 @@ class FrameDecoder {
         for (int i = 0; i < 3; i++) {
             const int fw = (f.padded_w >> 3) >> h.shift_x[i];
             const int y0 = (gy << 8) >> h.shift_y[i], x0 = (gx << 8) >> h.shift_x[i];
-            for (int y = 0; y < ch_h[i]; y++)
+            const Channel &q = ms.channels[kMap[i]];
+            for (int y = 0; y < ch_h[i]; y++) {
                 std::memcpy(&f.lf[i][(size_t)(y0 + y) * fw + x0], &dq[i][(size_t)y * ch_w[i]], sizeof(float) * ch_w[i]);
+                std::memcpy(&f.lf_quant[i][(size_t)(y0 + y) * fw + x0], &q.px[(size_t)y * ch_w[i]], sizeof(int32_t) * ch_w[i]);
+            }
         }
         // LF context index per block (:183-202)
         st.lf_index.assign((size_t)st.bh * st.bw, 0);

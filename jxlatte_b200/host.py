@@ -372,6 +372,20 @@ class Reconstructor:
         (cp, cpi), (ap, api), (bp, bpi), (fp, fpi), (rp, rpi) = rect(canvas), rect(a), rect(b), rect(fa), rect(ra)
         self._check(self._L.jxlb200_blend(self._h, C.byref(o), h, w, cp, cpi, ap, api, bp, bpi, fp, fpi, rp, rpi))
 
+    def dequantLF(self, lf_quant, extra_precision, scaled_dequant, kx, kb, cfl=True, smooth=True):
+        """LFCoefficients (J/frame/vardct/LFCoefficients.java:61-103, 113-179) on the device: quantised LF planes [3, hb, wb] in X, Y, B
+        order + extraPrecision per LF group -> the dequantised, smoothed `lf` planes of the reconstruction call."""
+        q = [_c(lf_quant[c], np.int32) for c in range(3)]
+        hb, wb = q[0].shape
+        ep = _c(np.asarray(extra_precision).reshape(-1), np.uint8)
+        if ep.size != ((hb + 255) // 256) * ((wb + 255) // 256) or any(a.shape != (hb, wb) for a in q):
+            raise ValueError("lf_quant planes must share a shape and extra_precision hold one byte per LF group")
+        sd = (C.c_float * 3)(*[float(v) for v in scaled_dequant])
+        out = np.empty((3, hb, wb), np.float32)
+        self._check(self._L.jxlb200_lf_dequant(self._h, hb, wb, sd, C.c_float(float(kx)), C.c_float(float(kb)), 1 if cfl else 0, 1 if smooth else 0,
+                                               _lib.planes([_ptr(a) for a in q]), _ptr(ep), _lib.planes([_ptr(out[c]) for c in range(3)])))
+        return out
+
     def blend_batch(self, planes, writable, items):
         """A frame's whole compositing in one call (jxlb200_blend_batch).  planes: 2-D C-contiguous 4-byte numpy arrays (written in
         place when writable[i]); items: (op dict, (h, w), [(plane index, y, x) or None] * 5) in the order canvas, `frame`, `ref`,

@@ -87,6 +87,9 @@ void orc_gab(const orc_frame_params *p, const float *const in[3], float *const o
 /* Frame.performEdgePreservingFilter (:544-636). buf[3] updated in place (ping-pong handled inside).
  * returns -2 on sharpness outside [0,7]. */
 int32_t orc_epf(const orc_frame_params *p, float *const buf[3], const int32_t *hf_mul, const int32_t *sharpness, int32_t nthreads);
+/* LFCoefficients.java:61-103, 113-179: LF dequantisation + LF chroma-from-luma + adaptive smoothing, per LF group */
+void orc_lf_dequant(int32_t hb, int32_t wb, const float scaled_dequant[3], float kx, float kb, int32_t cfl, int32_t smooth,
+                    const int32_t *const lf_quant[3], const uint8_t *extra_precision, float *const out[3]);
 /* Modular-encoded frames: one sigma for the frame (Frame.java:573-575, 604-607) */
 int32_t orc_epf_uniform(const orc_frame_params *p, float *const buf[3], float epf_sigma_for_modular, int32_t nthreads);
 /* JXLCodestreamDecoder.performColorTransforms (J/JXLCodestreamDecoder.java:256-283) */

@@ -163,6 +163,21 @@ def epf(p, planes, hf_mul, sharpness, nthreads=1):
     return np.stack(buf)
 
 
+def lf_dequant(lf_quant, extra_precision, scaled_dequant, kx, kb, cfl=True, smooth=True):
+    """LFCoefficients: quantised LF planes [3, hb, wb] (X, Y, B order) -> dequantised, LF chroma-from-luma, adaptive smoothing."""
+    L = lib()
+    q = [np.ascontiguousarray(lf_quant[c], np.int32) for c in range(3)]
+    hb, wb = q[0].shape
+    ep = np.ascontiguousarray(extra_precision, np.uint8).reshape(-1)
+    assert ep.size == ((hb + 255) // 256) * ((wb + 255) // 256)
+    sd = (C.c_float * 3)(*[float(v) for v in scaled_dequant])
+    out = [np.zeros((hb, wb), np.float32) for _ in range(3)]
+    L.orc_lf_dequant.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_lf_dequant.restype = None
+    L.orc_lf_dequant(hb, wb, sd, float(kx), float(kb), int(bool(cfl)), int(bool(smooth)), _planes(q, C.c_int32), ep.ctypes.data, _planes(out, C.c_float))
+    return np.stack(out)
+
+
 def epf_uniform(p, planes, sigma_for_modular, nthreads=1):
     """performEdgePreservingFilter on a Modular-encoded frame: invModularSigma = 1f / epfSigmaForModular everywhere."""
     L = lib()

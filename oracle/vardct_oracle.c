@@ -1661,3 +1661,69 @@ void orc_pack_samples(const void *const *planes, const int32_t *is_int, const in
             if (bytes == 2) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)(v & 255); } else o[0] = (uint8_t)v;
         }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * LF coefficients: dequantisation, LF chroma-from-luma, adaptive smoothing
+ * (J/frame/vardct/LFCoefficients.java:61-103 and adaptiveSmooth :113-179), per LF group (256 x 256 blocks).
+ * lf_quant[i]: frame-level hb x wb planes in FRAME order X, Y, B (i.e. lfQuant[cMap[i]] stitched over LF groups);
+ * extra_precision[g]: the 2 bits read per LF group; kx / kb: baseCorrelation + (factorLF - 128) / colorFactor (:81-82).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_lf_dequant(int32_t hb, int32_t wb, const float scaled_dequant[3], float kx, float kb, int32_t cfl, int32_t smooth,
+                    const int32_t *const lf_quant[3], const uint8_t *extra_precision, float *const out[3]) {
+    const int gcols = (wb + 255) >> 8, grows = (hb + 255) >> 8;
+    for (int gy = 0; gy < grows; gy++)
+        for (int gx = 0; gx < gcols; gx++) {
+            const int y0 = gy << 8, x0 = gx << 8;
+            const int h = hb - y0 < 256 ? hb - y0 : 256, w = wb - x0 < 256 ? wb - x0 : 256;
+            const int ep = extra_precision[gy * gcols + gx];
+            float *co[3], *weighted[3], *gap = (float *)malloc(sizeof(float) * (size_t)h * w);
+            for (int i = 0; i < 3; i++) {
+                co[i] = (float *)malloc(sizeof(float) * (size_t)h * w);
+                weighted[i] = (float *)calloc((size_t)h * w, sizeof(float));
+                const float sd = scaled_dequant[i] / (1 << ep);                       /* :67 */
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++)
+                        co[i][y * w + x] = lf_quant[i][(size_t)(y0 + y) * wb + x0 + x] * sd;   /* :72 */
+            }
+            if (cfl)                                                                    /* :77-94 */
+                for (int k = 0; k < h * w; k++) {
+                    co[0][k] += kx * co[1][k];
+                    co[2][k] += kb * co[1][k];
+                }
+            if (smooth && h >= 3 && w >= 3) {                                           /* adaptiveSmooth :113-179 */
+                for (int k = 0; k < h * w; k++) gap[k] = 0.5f;
+                for (int i = 0; i < 3; i++) {
+                    const float sd = scaled_dequant[i];
+                    for (int y = 1; y < h - 1; y++)
+                        for (int x = 1; x < w - 1; x++) {
+                            const float *c = co[i] + y * w + x;
+                            const float sample = c[0];
+                            const float adjacent = c[-1] + c[1] + c[-w] + c[w];
+                            const float diag = c[-w - 1] + c[-w + 1] + c[w - 1] + c[w + 1];
+                            const float wv = 0.05226273532324128f * sample + 0.20345139757231578f * adjacent + 0.0334829185968739f * diag;
+                            weighted[i][y * w + x] = wv;
+                            const float g = fabsf(sample - wv) * sd;
+                            if (g > gap[y * w + x]) gap[y * w + x] = g;
+                        }
+                }
+                for (int k = 0; k < h * w; k++) {
+                    const float v = 3.0f - 4.0f * gap[k];
+                    gap[k] = v > 0.0f ? v : 0.0f;                                       /* Math.max(0f, ...) :155 */
+                }
+                for (int i = 0; i < 3; i++)
+                    for (int y = 0; y < h; y++)
+                        for (int x = 0; x < w; x++) {
+                            const int k = y * w + x;
+                            float v = co[i][k];
+                            if (!(y == 0 || y + 1 == h || x == 0 || x + 1 == w)) v = (co[i][k] - weighted[i][k]) * gap[k] + weighted[i][k];
+                            out[i][(size_t)(y0 + y) * wb + x0 + x] = v;
+                        }
+            } else {
+                for (int i = 0; i < 3; i++)
+                    for (int y = 0; y < h; y++)
+                        for (int x = 0; x < w; x++) out[i][(size_t)(y0 + y) * wb + x0 + x] = co[i][y * w + x];
+            }
+            for (int i = 0; i < 3; i++) { free(co[i]); free(weighted[i]); }
+            free(gap);
+        }
+}

@@ -535,3 +535,46 @@ def test_modular_frame_filters_kernel_matches_oracle(recon, orc, cfg):
             want = orc.epf_uniform(p, want, sigma)
         got = recon.restoreModularFrame(p, planes, sigma)
         assert np.array_equal(got, want), "sigma %g: max abs err %g" % (sigma, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("name", ["lenna", "bbb"])
+def test_front_end_lf_equals_oracle_lf_dequant(orc, name):
+    """The quantised LF planes the front end now hands out, through the oracle's restatement of LFCoefficients.java:61-103,
+    113-179, must give the front end's own dequantised LF bit for bit (two independent restatements of the same Java)."""
+    p = _parse(name)
+    k = len(p.frames) - 1
+    lfq = p.lf_quantised(k)
+    assert lfq is not None
+    q, ep, sd, kx, kb, smooth = lfq
+    want = p.vardct_state(k)["lf"]
+    got = orc.lf_dequant(q, ep, sd, kx, kb, cfl=True, smooth=smooth)
+    assert np.array_equal(got, want)
+    p.close()
+
+
+def test_lf_dequant_oracle_properties(orc):
+    """A constant field is a fixed point of the smoothing; without smoothing and CfL it is q * scaledDequant / 2^extraPrecision."""
+    q = np.full((3, 20, 30), 7, np.int32)
+    sd = [np.float32(0.01), np.float32(0.02), np.float32(0.03)]
+    out = orc.lf_dequant(q, [1], sd, 0.0, 0.0, cfl=False, smooth=False)
+    for c in range(3):
+        assert np.array_equal(out[c], np.full((20, 30), np.float32(7) * (sd[c] / np.float32(2)), np.float32))
+    sm = orc.lf_dequant(q, [1], sd, 0.0, 0.0, cfl=False, smooth=True)
+    assert np.abs(sm - out).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(hb=300, wb=520, cfl=True, smooth=True), dict(hb=64, wb=64, cfl=True, smooth=False),
+                                 dict(hb=257, wb=2, cfl=False, smooth=True), dict(hb=5, wb=700, cfl=True, smooth=True)])
+def test_lf_dequant_kernel_matches_oracle(recon, orc, cfg):
+    """jxlb200_lf_dequant == orc_lf_dequant: several LF groups with their own extraPrecision, groups too small to smooth."""
+    rng = np.random.default_rng(cfg["hb"] + cfg["wb"])
+    hb, wb = cfg["hb"], cfg["wb"]
+    q = rng.integers(-900, 900, size=(3, hb, wb)).astype(np.int32)
+    ng = ((hb + 255) // 256) * ((wb + 255) // 256)
+    ep = rng.integers(0, 4, size=ng).astype(np.uint8)
+    sd = [np.float32(0.0021), np.float32(0.00037), np.float32(0.0011)]
+    kx, kb = np.float32(0.013), np.float32(1.0 + 3.0 / 84.0)
+    want = orc.lf_dequant(q, ep, sd, kx, kb, cfl=cfg["cfl"], smooth=cfg["smooth"])
+    got = recon.dequantLF(q, ep, sd, kx, kb, cfl=cfg["cfl"], smooth=cfg["smooth"])
+    assert np.array_equal(got, want), "max abs err %g" % np.abs(got - want).max()

@@ -638,6 +638,22 @@ int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     return ctx->fail(JXLB200_E_ARG, "unknown option or value");
 }
 
+// Page-lock a caller's buffer once (a Panama Arena segment is pageable: the pipelined host entry points copy from and to it six
+// times slower than from pinned memory).  The segment stays usable as ordinary memory; unregister before it is freed.
+int32_t jxlb200_host_register(jxlb200_ctx *ctx, void *ptr, uint64_t bytes) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!ptr || bytes == 0) return ctx->fail(JXLB200_E_ARG, "NULL or empty buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int32_t jxlb200_host_unregister(jxlb200_ctx *ctx, void *ptr) {
+    if (!ctx) return JXLB200_E_ARG;
+    if (!ptr) return ctx->fail(JXLB200_E_ARG, "NULL buffer");
+    CUDA_TRY(ctx, cudaHostUnregister(ptr));
+    return 0;
+}
+
 // diagnostic: the shared-reciprocal divide of k2_exact against __fdiv_rn on n operand pairs drawn like the kernel's (divisor 1..13,
 // numerators image-like and arbitrary bit patterns); *mismatches must come back 0
 int32_t jxlb200_selftest_divide(jxlb200_ctx *ctx, int64_t n, int32_t seed, int64_t *mismatches) {

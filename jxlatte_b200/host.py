@@ -135,6 +135,13 @@ class Reconstructor:
     def launch_count(self):
         return int(self._L.jxlb200_launch_count(self._h))
 
+    def host_register(self, array):
+        """Page-lock a numpy array in place (jxlb200_host_register); pair with host_unregister before the array is freed."""
+        self._check(self._L.jxlb200_host_register(self._h, C.c_void_p(array.ctypes.data), int(array.nbytes)))
+
+    def host_unregister(self, array):
+        self._check(self._L.jxlb200_host_unregister(self._h, C.c_void_p(array.ctypes.data)))
+
     def selftest_divide(self, n, seed=1):
         """Mismatches between stage 2's shared-reciprocal divide and __fdiv_rn on n operand pairs (must be 0)."""
         bad = C.c_int64(-1)

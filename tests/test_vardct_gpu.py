@@ -321,3 +321,20 @@ def test_shared_reciprocal_divide(recon):
     bit patterns -- every result must equal __fdiv_rn's bit for bit."""
     for seed in (1, 2, 3):
         assert recon.selftest_divide(1 << 26, seed) == 0
+
+
+@pytest.mark.gpu
+def test_registered_caller_buffers(recon, orc):
+    """jxlb200_host_register: a caller's ordinary (pageable) buffers page-locked in place, used by the pipelined host entry
+    point, then released -- same planes as ever."""
+    W, H = 264, 1032
+    p = default_frame_params(W, H, epf_iters=2)
+    st = dict(_state(W, H, 77, p))
+    st["qcoeff"] = np.array(st["qcoeff"], np.int32, order="C", copy=True)
+    out = np.empty((3, H, W), np.float32)
+    recon.host_register(st["qcoeff"]); recon.host_register(out)
+    try:
+        got = recon.reconstruct(p, st, out=out)
+    finally:
+        recon.host_unregister(st["qcoeff"]); recon.host_unregister(out)
+    assert np.array_equal(got, orc.vardct_reconstruct(p, st, nthreads=8))

@@ -146,6 +146,31 @@ def note(msg):
     sys.stderr.flush()
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: keep the process (and with it the pinned host buffers it allocates, first touch) on the NUMA node the
+    GPU hangs off, so that eight ranks' host<->device copies use both sockets' memory controllers and PCIe roots instead of
+    crossing the socket link.  Best effort; returns what it did for the bench line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "single NUMA node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no usable CPU on node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d CPUs)" % (node, len(cpus))
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 class Workload:
     """One workload's device-resident inputs and its step (one pass of the hot path over one batch)."""
 
@@ -238,11 +263,14 @@ def run_ours(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if numa:
+        note("NUMA: " + numa)
 
     rec = Reconstructor(local)
     if os.environ.get("JXLB200_STAGE2"):      # kernel-variant experiments (include/jxlb200.h: JXLB200_OPT_STAGE2); default 0
@@ -387,7 +415,8 @@ def run_ours(args):
         h2d = sum(int(v.numel() * v.element_size()) for v in hst.values())
         e2e = {"value": W * H * world / 1e6 / dt, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(hout.numel() * 4),
                "ms_per_step": dt * 1e3, "api": "jxlb200_vardct_reconstruct (host buffers, pinned; int32 coefficients in, float32 planes out: the reference's own layout)",
-               "ranks": world, "note": "every rank makes the call at once on its own GPU; value = all ranks' pixels / slowest rank's time"}
+               "ranks": world, "numa": numa,
+               "note": "every rank makes the call at once on its own GPU; value = all ranks' pixels / slowest rank's time"}
         # the same call with the coefficients narrowed to int16 by the caller (jxlb200_vardct_reconstruct_i16: half the upload,
         # identical planes); reported beside e2e, which stays on the reference's own int32 layout
         h16 = dict(hnp)

@@ -934,14 +934,11 @@ int32_t jxlb200_vardct_reconstruct_split_dev(jxlb200_ctx *ctx, const jxlb200_fra
         if ((rc = stage1(0, R))) return rc;
         return stage2(0, R, false, false);
     }
-    // 1. the boundary group rows first
-    const int G = 256;
-    const bool edges_first = R >= 3 * G;
-    if (edges_first) {
-        if ((rc = stage1(0, G))) return rc;
-        const int last0 = ((R - 1) / G) * G;                // first row of the last (possibly short) group row
-        if ((rc = stage1(last0, R - last0))) return rc;
-    } else if ((rc = stage1(0, R))) return rc;
+    // 1. stage 1 of the whole slab in one go.  (Running the two boundary group rows first, so that the exchange could start earlier,
+    // was measured and dropped: every extra stage-1 call costs ~0.3 ms of launch latency -- a dozen persistent launches --, more than
+    // the 0.1 ms exchange it would hide; the exchange hides behind stage 2 of the interior rows anyway.  8 B200s, 16384^2: 3.23 -> see
+    // profiles/r2_multigpu.md.)
+    if ((rc = stage1(0, R))) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_edge, main));
     // 2. halo rows and the neighbours' block rows, one NCCL group on the comm stream
     CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_edge, 0));
@@ -969,11 +966,7 @@ int32_t jxlb200_vardct_reconstruct_split_dev(jxlb200_ctx *ctx, const jxlb200_fra
     }
     NCCL_TRY(ctx, N.GroupEnd());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_halo, cs));
-    // 3. the rest of stage 1 and the rows of stage 2 that need no halo, beside the exchange
-    if (edges_first) {
-        const int last0 = ((R - 1) / G) * G;
-        if ((rc = stage1(G, last0 - G))) return rc;
-    }
+    // 3. stage 2 of the rows that need no halo, beside the exchange
     const int a = up ? HR : 0, b = down ? R - HR : R;
     if ((rc = stage2(a, b, up, down))) return rc;
     // 4. the rows next to the neighbours

@@ -3,12 +3,11 @@
 // frame; the halo rows travel with ncclSend / ncclRecv over NVLink on a side stream and overlap the slab's own work.
 //
 // Order of work in one call (slab of R rows, neighbours above and / or below):
-//   1. stage 1 of the slab's first and last group row (the rows the neighbours are waiting for)        main stream
+//   1. stage 1 of the slab                                                                               main stream
 //   2. send my 8 boundary rows up / down, receive the neighbours' (3 planes each, one NCCL group)        comm stream, after 1
-//   3. stage 1 of the group rows in between, then stage 2 of the rows that need no halo [8, R - 8)      main stream, beside 2
+//   3. stage 2 of the rows that need no halo [8, R - 8)                                                  main stream, beside 2
 //   4. stage 2 of the top 8 and bottom 8 rows once the halos are in                                     main stream, after 2
-// Varblocks never cross a group row (HFMetadata.placeBlock), so cutting stage 1 at group rows changes nothing; stage 2 of a
-// sub-range with has_top / has_bottom set reads its neighbour rows from the slab itself.  Bit-identical to the whole frame
+// Stage 2 of a sub-range with has_top / has_bottom set reads its neighbour rows from the slab itself.  Bit-identical to the whole frame
 // (tests/test_baseline_sizes_gpu.py::test_nccl_group_row_split_is_bit_identical).
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy already in the process -- PyTorch's, a JVM shim's -- or the

@@ -368,24 +368,25 @@ template <int GAB> K2S_FN void k2s_g_row(const K2SArgs &A, float *sm, K2SGabStat
 // T(y+1) from the one row it loads (y+1+DY) and the rows it kept; dist(y) = sum over c of T(y,x) + T(y,x-1) + T(y,x+1) + T(y-1,x)
 // + T(y+1,x), in that order.
 // ------------------------------------------------------------------------------------------------------------------------
-template <int DY> struct K2SDistState { float a[3][4], b[3][6], i1[3][DY > 0 ? 4 : 1], i2[3][DY > 1 ? 4 : 1]; };
-template <int DY, int DX, int RS_IN, int RS_OUT>
-K2S_FN void k2s_d_row(const K2Params &P, const float *in, float *outmap, K2SDistState<DY> &st, int S, int lane) {
+// ONE body for every canonical offset (dy, dx are run-time, warp-uniform): eight warps run it at once, and eight template instances
+// of it were 27 KB of hot code in front of a 32 KB instruction cache (profiles/r2_k2_stream_ncu.md).
+struct K2SDistState { float a[3][4], b[3][6], i1[3][4], i2[3][4]; };
+K2S_FN void k2s_d_row(const K2Params &P, const float *in_row, int plane_stride, float *out_row, int dy, int dx, K2SDistState &st, int lane) {
     float dist[4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const K2SQuad nq = k2s_ld4(in + (c * RS_IN + k2s_slot(S + 1 + DY, RS_IN)) * K2S_PITCH + 4 * lane);
+        const K2SQuad nq = k2s_ld4(in_row + c * plane_stride + 4 * lane);      // row y + 1 + dy
         const float nv[4] = {nq.x, nq.y, nq.z, nq.w};
         float base[4], sh[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) base[j] = DY == 0 ? nv[j] : st.i1[c][DY > 0 ? j : 0];
-        if (DX == 0) {
+        for (int j = 0; j < 4; j++) base[j] = dy == 0 ? nv[j] : st.i1[c][j];
+        if (dx == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) sh[j] = nv[j];
-        } else if (DX == 1) {
+        } else if (dx == 1) {
             const float e4 = k2s_dn(nv[0]);
             sh[0] = nv[1]; sh[1] = nv[2]; sh[2] = nv[3]; sh[3] = e4;
-        } else if (DX == 2) {
+        } else if (dx == 2) {
             const float e4 = k2s_dn(nv[0]), e5 = k2s_dn(nv[1]);
             sh[0] = nv[2]; sh[1] = nv[3]; sh[2] = e4; sh[3] = e5;
         } else {
@@ -407,18 +408,15 @@ K2S_FN void k2s_d_row(const K2Params &P, const float *in, float *outmap, K2SDist
             dist[j] = d;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) { st.a[c][j] = st.b[c][j + 1]; st.b[c][j + 1] = t[j]; }
-        st.b[c][0] = tl; st.b[c][5] = tr;
-        if (DY == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) st.i1[c][j] = nv[j];
-        } else if (DY == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) { st.i1[c][j] = st.i2[c][j]; st.i2[c][j] = nv[j]; }
+        for (int j = 0; j < 4; j++) {
+            st.a[c][j] = st.b[c][j + 1]; st.b[c][j + 1] = t[j];
+            st.i1[c][j] = dy == 2 ? st.i2[c][j] : nv[j];
+            st.i2[c][j] = nv[j];
         }
+        st.b[c][0] = tl; st.b[c][5] = tr;
     }
     K2SQuad q; q.x = dist[0]; q.y = dist[1]; q.z = dist[2]; q.w = dist[3];
-    k2s_st4(outmap + k2s_slot(S, RS_OUT) * K2S_PITCH + 4 * lane, q);
+    k2s_st4(out_row + 4 * lane, q);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -665,6 +663,7 @@ K2S_FN void k2s_role_g(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PAR
         // the rows this tick reads arrived with the loads of tick t-1
         if (t >= 1 && 8 * (t - 1) < total) k2s_mbar_wait(bars + ((t - 1) & 1), ((t - 1) >> 1) & 1);
 #endif
+#pragma unroll 1
         for (int r = 0; r < K2S_BAND; r++) {
             const int S = 8 * t + Cfg::G + r;
             // S == -1 primes the rolling window with stream row 0 (the row itself is not emitted)
@@ -674,21 +673,25 @@ K2S_FN void k2s_role_g(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PAR
     }
 }
 
-template <int DY, int DX, int RS_IN, int RS_OUT>
-K2S_FN void k2s_role_d(const K2SArgs &A, const float *in, float *outmap, int base, int n_ticks, int total, int lane) {
-    K2SDistState<DY> st;
+K2S_FN void k2s_role_d(const K2SArgs &A, const float *in, int rs_in, float *outmap, int rs_out, int dy, int dx, int base, int n_ticks, int total, int lane) {
+    K2SDistState st;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
 #pragma unroll
         for (int i = 0; i < 6; i++) st.b[c][i] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { st.a[c][i] = 0.0f; st.i1[c][DY > 0 ? i : 0] = 0.0f; st.i2[c][DY > 1 ? i : 0] = 0.0f; }
+        for (int i = 0; i < 4; i++) { st.a[c][i] = 0.0f; st.i1[c][i] = 0.0f; st.i2[c][i] = 0.0f; }
     }
+    const int plane_stride = rs_in * K2S_PITCH;
     for (int t = 0; t < n_ticks; t++) {
+        int si = k2s_slot(8 * t + base + 1 + dy, rs_in), so = k2s_slot(8 * t + base, rs_out);     // ring slots advance with the rows
+#pragma unroll 1
         for (int r = 0; r < K2S_BAND; r++) {
             const int S = 8 * t + base + r;
-            // steps -3 .. -1 prime the rolling rows (row r is loaded at step r - 1 - DY); what they store lands in ring slots nobody has used yet
-            if (S >= -3 && S < total) k2s_d_row<DY, DX, RS_IN, RS_OUT>(A.P, in, outmap, st, S, lane);
+            // steps -3 .. -1 prime the rolling rows (row r is loaded at step r - 1 - dy); what they store lands in ring slots nobody has used yet
+            if (S >= -3 && S < total) k2s_d_row(A.P, in + si * K2S_PITCH, plane_stride, outmap + so * K2S_PITCH, dy, dx, st, lane);
+            si = si + 1 == rs_in ? 0 : si + 1;
+            so = so + 1 == rs_out ? 0 : so + 1;
         }
         k2s_sync();
     }
@@ -720,21 +723,26 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
         //  role:  W0 W0 W0 W0| D0 D0 D0 D0| P2 P2 W1 W1 | D0 D0 P2 G  | D1 D1
         if (warp < 4) {
             for (int t = 0; t < n_ticks; t++) {
+#pragma unroll 1
                 for (int r = 0; r < 2; r++) {
                     const int S = 8 * t + Cfg::W0 + 2 * warp + r;
                     if (S >= 0 && S < total) k2s_w0_row(A, sm, cur, S, lane);
                 }
                 k2s_sync();
             }
-        } else if (warp == 4) k2s_role_d<0, 1, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 0 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
-        else if (warp == 5) k2s_role_d<1, 0, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 1 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
-        else if (warp == 6) k2s_role_d<1, 1, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 2 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
-        else if (warp == 7) k2s_role_d<1, -1, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 3 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
-        else if (warp == 12) k2s_role_d<0, 2, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 4 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
-        else if (warp == 13) k2s_role_d<2, 0, K2S_RS_GAB, K2S_RS_D0>(A, gab, d0 + 5 * K2S_RS_D0 * K2S_PITCH, Cfg::D0, n_ticks, total, lane);
+        } else if ((warp >= 4 && warp < 8) || warp == 12 || warp == 13 || warp >= 16) {
+            // distance roles: pass 0 offsets (0,1) (1,0) (1,1) (1,-1) (0,2) (2,0) on warps 4-7, 12, 13; pass 1 offsets (0,1) (1,0) on warps 16, 17
+            const bool p1 = warp >= 16;
+            const int m = p1 ? warp - 16 : (warp < 8 ? warp - 4 : warp - 8);          // map index
+            const int dy = p1 ? m : (m == 0 || m == 4 ? 0 : (m == 5 ? 2 : 1));
+            const int dx = p1 ? 1 - m : (m == 0 ? 1 : m == 2 ? 1 : m == 3 ? -1 : m == 4 ? 2 : 0);
+            k2s_role_d(A, p1 ? in1 : gab, p1 ? RS1 : K2S_RS_GAB, p1 ? d1 + m * K2S_RS_D1 * K2S_PITCH : d0 + m * K2S_RS_D0 * K2S_PITCH,
+                       p1 ? K2S_RS_D1 : K2S_RS_D0, dy, dx, p1 ? Cfg::D1 : Cfg::D0, n_ticks, total, lane);
+        }
         else if (warp == 8 || warp == 9 || warp == 14) {
             const int first = warp == 8 ? 0 : warp == 9 ? 3 : 6, count = warp == 14 ? 2 : 3;
             for (int t = 0; t < n_ticks; t++) {
+#pragma unroll 1
                 for (int r = 0; r < count; r++) {
                     const int S = 8 * t + Cfg::P2 + first + r;
                     if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
@@ -743,21 +751,21 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             }
         } else if (warp == 10 || warp == 11) {
             for (int t = 0; t < n_ticks; t++) {
+#pragma unroll 1
                 for (int r = 0; r < 4; r++) {
                     const int S = 8 * t + Cfg::W1 + 4 * (warp - 10) + r;
                     if (S >= 0 && S < total) k2s_w1_row<RS1, false>(A, sm, in1, cur, S, lane);
                 }
                 k2s_sync();
             }
-        } else if (warp == 15) k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);
-        else if (warp == 16) k2s_role_d<0, 1, RS1, K2S_RS_D1>(A, in1, d1, Cfg::D1, n_ticks, total, lane);
-        else k2s_role_d<1, 0, RS1, K2S_RS_D1>(A, in1, d1 + K2S_RS_D1 * K2S_PITCH, Cfg::D1, n_ticks, total, lane);
+        } else k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);      // warp 15
     } else {
         //  warp:  0  1  2  3 | 4  5  6  7 | 8  9  10        (epf_iters 2: W1 x4 then P2 x4;  epf_iters 1: W1 x8, the last stage)
         //  role:  W1 W1 W1 W1| P2 P2 P2 P2| D1 D1 G
         if (warp < 8 && (ITERS == 1 || warp < 4)) {
             constexpr int per = ITERS == 1 ? 1 : 2;
             for (int t = 0; t < n_ticks; t++) {
+#pragma unroll 1
                 for (int r = 0; r < per; r++) {
                     const int S = 8 * t + Cfg::W1 + per * warp + r;
                     if (S >= 0 && S < total) k2s_w1_row<RS1, ITERS == 1>(A, sm, in1, cur, S, lane);
@@ -766,15 +774,17 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             }
         } else if (warp < 8) {
             for (int t = 0; t < n_ticks; t++) {
+#pragma unroll 1
                 for (int r = 0; r < 2; r++) {
                     const int S = 8 * t + Cfg::P2 + 2 * (warp - 4) + r;
                     if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
                 }
                 k2s_sync();
             }
-        } else if (warp == 8) k2s_role_d<0, 1, RS1, K2S_RS_D1>(A, in1, d1, Cfg::D1, n_ticks, total, lane);
-        else if (warp == 9) k2s_role_d<1, 0, RS1, K2S_RS_D1>(A, in1, d1 + K2S_RS_D1 * K2S_PITCH, Cfg::D1, n_ticks, total, lane);
-        else k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);
+        } else if (warp == 8 || warp == 9) {
+            const int m = warp - 8;
+            k2s_role_d(A, in1, RS1, d1 + m * K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, m, 1 - m, Cfg::D1, n_ticks, total, lane);
+        } else k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);
     }
 }
 

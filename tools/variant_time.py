@@ -12,6 +12,9 @@ dev = torch.device("cuda", 0)
 rec = Reconstructor(0)
 s = torch.cuda.Stream(device=dev); torch.cuda.set_stream(s); rec.set_stream(s.cuda_stream)
 rec.setWeights(qw, qo)
+if os.environ.get("JXLB200_STAGE2"):
+    from jxlatte_b200 import _lib
+    rec.set_option(_lib.OPT_STAGE2, int(os.environ["JXLB200_STAGE2"]))
 d = {k: torch.from_numpy(np.ascontiguousarray(st[k])).to(dev) for k in ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")}
 out = torch.empty((3, H, W), dtype=torch.float32, device=dev)
 xyb = torch.empty((3, H, W), dtype=torch.float32, device=dev)

@@ -1,5 +1,5 @@
-// k2_stream.cuh -- K2 as a persistent, warp-specialised STREAM: Gaborish -> EPF pass 0 / 1 / 2 -> colour transform in one kernel,
-// bit-identical to the reference (every float operation in the reference's order, uncontracted).
+// k2_stream.cuh -- K2 as a persistent STREAM of rows: Gaborish -> EPF pass 0 / 1 / 2 -> colour transform in one kernel, bit-identical
+// to the reference (every float operation in the reference's order, uncontracted).
 //
 // Replaces Frame.performGabConvolution (J/frame/Frame.java:505-542), Frame.performEdgePreservingFilter (:544-679, epfDistance1
 // :638-655, epfDistance2 :657-669, epfWeight :671-679) and JXLCodestreamDecoder.performColorTransforms
@@ -7,29 +7,30 @@
 //
 // Shape of the computation (why it is not a tile kernel).  The filters are issue-bound, not HBM-bound, so the design
 // minimises INSTRUCTIONS per pixel, then shared-memory wavefronts:
-//   * a CTA (one per SM, persistent) walks column strips of the frame, 112 useful pixels wide (+8 halo columns each side = 128 =
-//     32 lanes x 4 pixels), top to bottom, in "items" of CH rows + 8 halo rows each side; the rows of all its items form one
+//   * a CTA (one per SM, persistent, 16 warps) walks column strips of the frame, 112 useful pixels wide (+8 halo columns each side =
+//     128 = 32 lanes x 4 pixels), top to bottom, in "items" of CH rows + 8 halo rows each side; the rows of all its items form one
 //     continuous stream of rows S = 0, 1, 2, ...  Nothing is recomputed vertically inside an item (a tile kernel recomputes its
 //     7-row halo per tile: +29 % at 64x48).
-//   * each stage of the chain is a ROLE held by dedicated warps; all roles run concurrently, each on its own 8-row band of the
-//     stream, a fixed number of rows behind its producer, and hand rows to each other through ring buffers in shared memory.
-//     One bar.sync per 8-row tick is the only synchronisation (plus the mbarrier the TMA loads complete on).
-//         TMA (cp.async.bulk.tensor, 4-row boxes)  -> RAW ring
-//         G   Gaborish (or copy)                   -> GAB ring          1 warp, rolling 3-row window in registers
-//         D0  pass-0 distances, one warp per canonical offset d in {(0,1),(1,0),(1,1),(1,-1),(0,2),(2,0)} -> six distance maps
-//         W0  pass-0 weights, sums, divide         -> P0 ring           4 warps
-//         D1  pass-1 distances, d in {(0,1),(1,0)} -> two distance maps 2 warps
-//         W1  pass-1 weights, sums, divide         -> P1 ring           2 warps (the last stage when epf_iters == 1)
-//         P2  pass 2 + colour transform + store    -> HBM               3 warps
+//   * the stages hand rows to each other through ring buffers in shared memory.  A TICK advances every stage by 16 rows, one stage
+//     after the other (PHASES separated by a CTA barrier), each stage a fixed number of rows behind its producer; inside a phase all
+//     16 warps run the same code, one row (or one pair of distance-map rows) each.  [Round 2's first version ran the stages
+//     CONCURRENTLY on dedicated warps; twelve loop bodies at once overflowed the 32 KB instruction cache -- profiles/r2_k2_stream_ncu.md.]
+//         TMA (cp.async.bulk.tensor, 4-row boxes)  -> RAW ring          issued a tick ahead, lands behind an mbarrier
+//         G   Gaborish (or copy)                   -> GAB ring          16 rows
+//         D0  pass-0 distances, d in {(0,1),(1,0),(1,1),(1,-1),(0,2),(2,0)} -> six distance maps, 48 row pairs
+//         W0  pass-0 weights, sums, divide         -> P0 ring           16 rows
+//         D1  pass-1 distances, d in {(0,1),(1,0)} -> two distance maps 16 row pairs
+//         W1  pass-1 weights, sums, divide         -> P1 ring           16 rows (the last stage when epf_iters == 1)
+//         P2  pass 2 + colour transform + store    -> HBM               16 rows
 //   * a lane owns a 4-pixel quad of a row; its neighbours' values come from the neighbour lanes by shuffle, so every row is read
 //     with one conflict-free 128-bit shared load per channel and the 4-way bank conflicts of strided scalar loads never occur.
 //   * what is shared without changing a rounding (as in k2_exact.cuh): the 15 terms of epfDistance1 are
-//     T_{c,d}(q) = fl(fl|I_c(q) - I_c(q+d)| * s_c), formed ONCE per position by the D warps and kept in registers as a rolling
-//     3-row window; dist_{-d}(p) == dist_d(p-d) operation for operation, so six (two) maps serve the twelve (four) offsets; the
-//     centre tap has weight exactly 1.  The ordered sums are literal.
+//     T_{c,d}(q) = fl(fl|I_c(q) - I_c(q+d)| * s_c), formed once per row pair and position by the D phases (4 T rows for 2 map rows);
+//     dist_{-d}(p) == dist_d(p-d) operation for operation, so six (two) maps serve the twelve (four) offsets; the centre tap has
+//     weight exactly 1.  The ordered sums are literal.
 //   * frame edges: MathHelper.mirrorCoordinate (J/util/MathHelper.java:323-329) applies to a stage's OUTPUT.  Rows above the
 //     frame are written behind the producer when their mirror source row is produced (they lie in the item's own upper halo);
-//     rows below are copied from behind when the producer reaches them; columns are mirrored across lanes before the store.
+//     rows below are copied from behind after the phase's barrier; columns are mirrored across lanes before the store.
 //
 // The same source compiles for the host (K2S_HOST_EMU, tests/host/k2_stream_host.cpp): 32 host threads per warp, the shuffles and
 // barriers emulated, so tests/test_k2_stream_host.py holds the whole stream -- ring arithmetic, lags, mirror handling, operation
@@ -44,25 +45,36 @@
 #define K2S_ADD(a, b) ((a) + (b))   /* host build uses -ffp-contract=off */
 #define K2S_SUB(a, b) ((a) - (b))
 #define K2S_MUL(a, b) ((a) * (b))
-#define K2S_DIV(a, b) ((a) / (b))
+#define K2S_RCP(b) (0.0f)
+#define K2S_DIVS(a, b, r) ((a) / (b))
 #define K2S_LDG(p) (*(p))
 #else
 #include <cuda.h>
+#include "k2_exact.cuh"             /* kx_rcp_refined / kx_div_shared: the three divides of a pixel share one refined reciprocal */
 #define K2S_FN __device__ __forceinline__
 #define K2S_ADD(a, b) __fadd_rn((a), (b))
 #define K2S_SUB(a, b) __fsub_rn((a), (b))
 #define K2S_MUL(a, b) __fmul_rn((a), (b))
-#define K2S_DIV(a, b) __fdiv_rn((a), (b))
+#define K2S_RCP(b) kx_rcp_refined(b)
+#define K2S_DIVS(a, b, r) kx_div_shared((a), (b), (r))
 #define K2S_LDG(p) __ldg(p)
 #endif
 
+#ifdef K2S_UNROLL_CHANNELS
+#define K2S_ROLLED_TRIPS(P) 3
+#else
+#define K2S_ROLLED_TRIPS(P) ((P).W > 0 ? 3 : 0)
+#endif
 #define K2S_TW 112            /* useful columns of a column strip */
 #define K2S_HALO 8            /* halo columns each side and halo rows each side of an item (7 used: 1 + 3 + 2 + 1) */
 #define K2S_PITCH 128         /* floats per ring row: 32 lanes x 4 */
-#define K2S_BAND 8            /* rows per tick */
+#define K2S_BAND 16           /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase */
+#define K2S_NWARPS 16
+// Ring sizes in rows.  Within a tick the writer of a ring runs before its readers; a ring must hold the rows its readers still need
+// when the writer's next band lands on top of the oldest slots (worked out row by row in DESIGN.md).
 #define K2S_RS_RAW 20
-#define K2S_RS_GAB 34
-#define K2S_RS_P0 30
+#define K2S_RS_GAB 24
+#define K2S_RS_P0 20
 #define K2S_RS_P1 18
 #define K2S_RS_D0 18
 #define K2S_RS_D1 17
@@ -93,28 +105,19 @@ struct K2SArgs {
     int tma_row0;               // tensor-map row of frame row 0 (8 when the slab has rows above it)
 };
 
-// Stage s processes stream rows [8t + base_s, 8t + base_s + 8) in tick t.  A consumer trails its producer by one band (what
-// it reads was complete before the tick began) plus the rows below its own that it reads.  The D roles trail further: a D warp
-// loads row r at step r - 1 - DY (rolling window), and a row above the frame exists only once its mirror source row k - 1 has been
-// produced (k <= margin), 2k + DY rows later in stream order: 8 more rows behind G, 5 more behind W0.
-// The W bases are also chosen modulo 8: a row below the frame is a copy of its mirror row (k2s_copy_behind), and the warp that copies
-// must not run ahead of the warp that produces the source within a tick.  Items start on multiples of 8, so a band covers frame rows
-// y == base .. base + 7 (mod 8) and the frame's last row is == 7: with W0 == 7 (mod 8) and two rows per warp the pair (rows-1, rows) is
-// one warp's and (rows-2, rows+1) straddles two ticks; with W1 == 2 (mod 8) and four rows per warp, or 1 (mod 8) and two rows per
-// warp, rows-1 and rows are one warp's again.
+// In tick t a stage processes stream rows [16t + base, 16t + base + 16); the TMA loads of tick t bring rows [16t, 16t + 16).
+// A stage trails its producer by the rows below its own that it reads, and by one more where a row ABOVE the frame is involved: such a
+// row exists only once its mirror source has been produced (row -k is written together with row k-1).  D0 evaluates map rows down to
+// y = -2 (pass 0 at row 0 uses dist_(2,0) at row -2), which read GAB rows down to -3, written with GAB row 2 = y + 4.
+//   G reads RAW rows S-1 .. S+1                        -> G  = -2
+//   D0 reads GAB rows S-1 .. S+3 (and see above)       -> D0 = G - 4;  W0 reads GAB S-2 .. S+2 and the maps S-2 .. S -> W0 = D0
+//   D1 reads P0 rows S-1 .. S+2                        -> D1 = W0 - 2; W1 = D1
+//   P2 reads P1 rows S-1 .. S+1                        -> P2 = W1 - 1
+// epf_iters < 3: pass 1 reads the GAB ring: D1 = W1 = G - 2.
 template <int ITERS> struct K2SCfg;
-template <> struct K2SCfg<3> {
-    static constexpr int G = -9, D0 = -25, W0 = -33, D1 = -46, W1 = -54, P2 = -63, LAST = -63;
-    static constexpr int NWARPS = 18;
-};
-template <> struct K2SCfg<2> {
-    static constexpr int G = -9, D0 = 0, W0 = 0, D1 = -23, W1 = -31, P2 = -40, LAST = -40;
-    static constexpr int NWARPS = 11;
-};
-template <> struct K2SCfg<1> {
-    static constexpr int G = -9, D0 = 0, W0 = 0, D1 = -23, W1 = -31, P2 = 0, LAST = -31;
-    static constexpr int NWARPS = 11;
-};
+template <> struct K2SCfg<3> { static constexpr int G = -2, D0 = -6, W0 = -6, D1 = -8, W1 = -8, P2 = -9, LAST = -9; };
+template <> struct K2SCfg<2> { static constexpr int G = -2, D0 = 0, W0 = 0, D1 = -4, W1 = -4, P2 = -5, LAST = -5; };
+template <> struct K2SCfg<1> { static constexpr int G = -2, D0 = 0, W0 = 0, D1 = -4, W1 = -4, P2 = 0, LAST = -4; };
 
 // ------------------------------------------------------------------------------------------------------------------------
 // platform layer: lane id, shuffles, CTA barrier, TMA.  Host versions live in tests/host/k2_stream_host.cpp.
@@ -125,6 +128,7 @@ int k2s_emu_cta();
 int k2s_emu_grid();
 float k2s_emu_shfl(float v, int src_lane);
 void k2s_emu_sync();
+int k2s_emu_sync_or(int pred);
 struct K2STmap { const float *base; int w, rows; long long pitch; };
 K2S_FN int k2s_tid() { return k2s_emu_tid(); }
 K2S_FN int k2s_cta() { return k2s_emu_cta(); }
@@ -133,6 +137,7 @@ K2S_FN float k2s_up(float v) { const int l = k2s_emu_tid() & 31; return k2s_emu_
 K2S_FN float k2s_dn(float v) { const int l = k2s_emu_tid() & 31; return k2s_emu_shfl(v, l < 31 ? l + 1 : l); }
 K2S_FN float k2s_from(float v, int src) { return k2s_emu_shfl(v, src); }
 K2S_FN void k2s_sync() { k2s_emu_sync(); }
+K2S_FN int k2s_sync_or(int pred) { return k2s_emu_sync_or(pred); }
 struct K2SQuad { float x, y, z, w; };
 K2S_FN K2SQuad k2s_ld4(const float *p) { return K2SQuad{p[0], p[1], p[2], p[3]}; }
 K2S_FN void k2s_st4(float *p, K2SQuad q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
@@ -155,8 +160,8 @@ K2S_FN int k2s_grid() { return gridDim.x; }
 K2S_FN float k2s_up(float v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 K2S_FN float k2s_dn(float v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 K2S_FN float k2s_from(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-// every warp of the CTA arrives at barrier 0 once per tick, each from its own role's loop
-K2S_FN void k2s_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+K2S_FN void k2s_sync() { __syncthreads(); }
+K2S_FN int k2s_sync_or(int pred) { return __syncthreads_or(pred); }
 K2S_FN K2SQuad k2s_ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 K2S_FN void k2s_st4(float *p, K2SQuad q) { *reinterpret_cast<float4 *>(p) = q; }
 K2S_FN void k2s_stg4(float *p, K2SQuad q) { *reinterpret_cast<float4 *>(p) = q; }
@@ -317,120 +322,128 @@ K2S_FN float k2s_sigma(const K2SArgs &A, const K2SRow &R, int lane, float m[4]) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// G: Gaborish (Frame.java:505-542) of stream row S into the GAB ring; one warp, rolling window: rows y-1 and y stay in registers
-// with their west / east neighbours, row y+1 is the one load of the step.  Edge = clamp on the padded plane (:526-534).
+// G: Gaborish (Frame.java:505-542) of stream row S into the GAB ring: rows S-1, S, S+1 of the RAW ring, west / east neighbours by
+// shuffle.  Edge = clamp on the padded plane (:526-534): at the frame's first / last row the row itself stands in for the missing
+// one, at the first / last column the lane's own outer pixel.  Returns the row's kind (k2s_row_kind).
 // ------------------------------------------------------------------------------------------------------------------------
-struct K2SGabState { float n[3][6], r[3][6]; };
-template <int GAB> K2S_FN void k2s_g_row(const K2SArgs &A, float *sm, K2SGabState &st, K2SCursor &cur, int S, int lane) {
+template <int GAB> K2S_FN int k2s_g_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
     const K2Params &P = A.P;
     const K2SRow R = k2s_at(A, cur, S);
-    const float *raw = sm + K2S_OFF_RAW;
+    if (!R.valid) return 1;
+    const int kind = k2s_row_kind(P, R.y, K2S_MARGIN_GAB);
+    if (kind != 0) return kind;
+    const float *raw = sm + K2S_OFF_RAW + 4 * lane;
     float *gab = sm + K2S_OFF_GAB;
+    const int sr = k2s_slot(S, K2S_RS_RAW);
     K2SQuad out[3];
     if (!GAB) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) out[c] = k2s_ld4(raw + (c * K2S_RS_RAW + k2s_slot(S, K2S_RS_RAW)) * K2S_PITCH + 4 * lane);
+        for (int c = 0; c < 3; c++) out[c] = k2s_ld4(raw + (c * K2S_RS_RAW + sr) * K2S_PITCH);
     } else {
         const int col = R.x0 - K2S_HALO + 4 * lane;
         const bool first_col = col == 0, last_col = col + 4 == P.W;
         const bool clamp_n = R.y == 0 && !P.has_top, clamp_s = R.y == P.rows - 1 && !P.has_bottom;
+        const int sn = clamp_n ? sr : (sr == 0 ? K2S_RS_RAW - 1 : sr - 1), ss = clamp_s ? sr : (sr + 1 == K2S_RS_RAW ? 0 : sr + 1);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const K2SQuad q = k2s_ld4(raw + (c * K2S_RS_RAW + k2s_slot(S + 1, K2S_RS_RAW)) * K2S_PITCH + 4 * lane);
-            float s6[6] = {k2s_up(q.w), q.x, q.y, q.z, q.w, k2s_dn(q.x)};
-            if (first_col) s6[0] = s6[1];
-            if (last_col) s6[5] = s6[4];
+            const K2SQuad qn = k2s_ld4(raw + (c * K2S_RS_RAW + sn) * K2S_PITCH), qr = k2s_ld4(raw + (c * K2S_RS_RAW + sr) * K2S_PITCH);
+            const K2SQuad qs = k2s_ld4(raw + (c * K2S_RS_RAW + ss) * K2S_PITCH);
+            float n6[6] = {k2s_up(qn.w), qn.x, qn.y, qn.z, qn.w, k2s_dn(qn.x)};
+            float r6[6] = {k2s_up(qr.w), qr.x, qr.y, qr.z, qr.w, k2s_dn(qr.x)};
+            float s6[6] = {k2s_up(qs.w), qs.x, qs.y, qs.z, qs.w, k2s_dn(qs.x)};
+            if (first_col) { n6[0] = n6[1]; r6[0] = r6[1]; s6[0] = s6[1]; }
+            if (last_col) { n6[5] = n6[4]; r6[5] = r6[4]; s6[5] = s6[4]; }
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float *Rr = st.r[c];
-                const float nw = clamp_n ? Rr[j] : st.n[c][j], nx = clamp_n ? Rr[j + 1] : st.n[c][j + 1], ne = clamp_n ? Rr[j + 2] : st.n[c][j + 2];
-                const float sw = clamp_s ? Rr[j] : s6[j], sx = clamp_s ? Rr[j + 1] : s6[j + 1], se = clamp_s ? Rr[j + 2] : s6[j + 2];
                 // Frame.java:535-537: operand order kept, uncontracted
-                const float adj = K2S_ADD(K2S_ADD(K2S_ADD(Rr[j], Rr[j + 2]), nx), sx);
-                const float diag = K2S_ADD(K2S_ADD(K2S_ADD(nw, ne), sw), se);
-                o[j] = K2S_ADD(K2S_ADD(K2S_MUL(P.gab_base[c], Rr[j + 1]), K2S_MUL(P.gab_adj[c], adj)), K2S_MUL(P.gab_diag[c], diag));
+                const float adj = K2S_ADD(K2S_ADD(K2S_ADD(r6[j], r6[j + 2]), n6[j + 1]), s6[j + 1]);
+                const float diag = K2S_ADD(K2S_ADD(K2S_ADD(n6[j], n6[j + 2]), s6[j]), s6[j + 2]);
+                o[j] = K2S_ADD(K2S_ADD(K2S_MUL(P.gab_base[c], r6[j + 1]), K2S_MUL(P.gab_adj[c], adj)), K2S_MUL(P.gab_diag[c], diag));
             }
             out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
-#pragma unroll
-            for (int i = 0; i < 6; i++) { st.n[c][i] = st.r[c][i]; st.r[c][i] = s6[i]; }
         }
     }
-    if (!R.valid) return;
-    const int kind = k2s_row_kind(P, R.y, K2S_MARGIN_GAB);
-    if (kind == 0) k2s_emit(P, gab, K2S_RS_GAB, K2S_MARGIN_GAB, R, S, lane, out);
-    else if (kind == 2) k2s_copy_behind(P, gab, K2S_RS_GAB, R, S, lane);
+    k2s_emit(P, gab, K2S_RS_GAB, K2S_MARGIN_GAB, R, S, lane, out);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// D: the distance map of one canonical offset d = (DY, DX) for stream row S (epfDistance1, Frame.java:638-655).
-// T(q) = fl(fl|I(q) - I(q+d)| * s_c).  Rolling: A = T(y-1) (own 4 columns), B = T(y) (columns x-1 .. x+4), this step forms
-// T(y+1) from the one row it loads (y+1+DY) and the rows it kept; dist(y) = sum over c of T(y,x) + T(y,x-1) + T(y,x+1) + T(y-1,x)
-// + T(y+1,x), in that order.
+// D: rows S0 and S0+1 of the distance map of one canonical offset d = (DY, DX) (epfDistance1, Frame.java:638-655).
+// T(q) = fl(fl|I(q) - I(q+d)| * s_c) for the four rows S0-1 .. S0+2 (input rows S0-1 .. S0+2+DY, one 128-bit load each; the shifted
+// row's columns come from the neighbour lanes), then dist(y) = sum over c of T(y,x) + T(y,x-1) + T(y,x+1) + T(y-1,x) + T(y+1,x), in
+// that order.  Every stream row is evaluated, inside the frame or not: the input ring carries the mirrored rows and columns.
 // ------------------------------------------------------------------------------------------------------------------------
-// ONE body for every canonical offset (dy, dx are run-time, warp-uniform): eight warps run it at once, and eight template instances
-// of it were 27 KB of hot code in front of a 32 KB instruction cache (profiles/r2_k2_stream_ncu.md).
-struct K2SDistState { float a[3][4], b[3][6], i1[3][4], i2[3][4]; };
-K2S_FN void k2s_d_row(const K2Params &P, const float *in_row, int plane_stride, float *out_row, int dy, int dx, K2SDistState &st, int lane) {
-    float dist[4];
+template <int DY, int DX> K2S_FN void k2s_d_pair(const K2Params &P, const float *in, int rs_in, float *outmap, int rs_out, int S0, int lane) {
+    float dist[2][4];
+    int slot[4 + DY];
+    slot[0] = k2s_slot(S0 - 1, rs_in);
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const K2SQuad nq = k2s_ld4(in_row + c * plane_stride + 4 * lane);      // row y + 1 + dy
-        const float nv[4] = {nq.x, nq.y, nq.z, nq.w};
-        float base[4], sh[4];
+    for (int i = 1; i < 4 + DY; i++) slot[i] = slot[i - 1] + 1 == rs_in ? 0 : slot[i - 1] + 1;
 #pragma unroll
-        for (int j = 0; j < 4; j++) base[j] = dy == 0 ? nv[j] : st.i1[c][j];
-        if (dx == 0) {
+    for (int k = 0; k < 2; k++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) sh[j] = nv[j];
-        } else if (dx == 1) {
-            const float e4 = k2s_dn(nv[0]);
-            sh[0] = nv[1]; sh[1] = nv[2]; sh[2] = nv[3]; sh[3] = e4;
-        } else if (dx == 2) {
-            const float e4 = k2s_dn(nv[0]), e5 = k2s_dn(nv[1]);
-            sh[0] = nv[2]; sh[1] = nv[3]; sh[2] = e4; sh[3] = e5;
-        } else {
-            const float em = k2s_up(nv[3]);
-            sh[0] = em; sh[1] = nv[0]; sh[2] = nv[1]; sh[3] = nv[2];
+        for (int j = 0; j < 4; j++) dist[k][j] = 0.0f;
+    // the channel loop stays rolled (trip count read from a kernel argument, or the compiler unrolls it whatever the pragma says): the
+    // D0 phase runs six instances of this body at once, and unrolled they are two instruction caches' worth of code
+    const int nch = K2S_ROLLED_TRIPS(P);
+#pragma unroll 1
+    for (int c = 0; c < nch; c++) {
+        const float *pl = in + c * rs_in * K2S_PITCH + 4 * lane;
+        float I[4 + DY][4];
+#pragma unroll
+        for (int i = 0; i < 4 + DY; i++) {
+            const K2SQuad q = k2s_ld4(pl + slot[i] * K2S_PITCH);
+            I[i][0] = q.x; I[i][1] = q.y; I[i][2] = q.z; I[i][3] = q.w;
         }
         const float s = P.ch_scale[c];
-        float t[4];
+        float T[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) t[j] = K2S_MUL(fabsf(K2S_SUB(base[j], sh[j])), s);
-        const float tl = k2s_up(t[3]), tr = k2s_dn(t[0]);
+        for (int r = 0; r < 4; r++) {
+            const float *b = I[r], *v = I[r + DY];
+            float sh[4];
+            if (DX == 0) { sh[0] = v[0]; sh[1] = v[1]; sh[2] = v[2]; sh[3] = v[3]; }
+            else if (DX == 1) { sh[0] = v[1]; sh[1] = v[2]; sh[2] = v[3]; sh[3] = k2s_dn(v[0]); }
+            else if (DX == 2) { sh[0] = v[2]; sh[1] = v[3]; sh[2] = k2s_dn(v[0]); sh[3] = k2s_dn(v[1]); }
+            else { sh[0] = k2s_up(v[3]); sh[1] = v[0]; sh[2] = v[1]; sh[3] = v[2]; }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float d = c == 0 ? st.b[c][j + 1] : K2S_ADD(dist[j], st.b[c][j + 1]);   // (0, 0); the running sum starts at 0f and 0 + t == t
-            d = K2S_ADD(d, st.b[c][j]);                                             // (0, -1)
-            d = K2S_ADD(d, st.b[c][j + 2]);                                         // (0, +1)
-            d = K2S_ADD(d, st.a[c][j]);                                             // (-1, 0)
-            d = K2S_ADD(d, t[j]);                                                   // (+1, 0)
-            dist[j] = d;
+            for (int j = 0; j < 4; j++) T[r][j] = K2S_MUL(fabsf(K2S_SUB(b[j], sh[j])), s);
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            st.a[c][j] = st.b[c][j + 1]; st.b[c][j + 1] = t[j];
-            st.i1[c][j] = dy == 2 ? st.i2[c][j] : nv[j];
-            st.i2[c][j] = nv[j];
+        for (int k = 0; k < 2; k++) {
+            const float *t = T[k + 1];
+            const float t6[6] = {k2s_up(t[3]), t[0], t[1], t[2], t[3], k2s_dn(t[0])};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float d = K2S_ADD(dist[k][j], t6[j + 1]);                      // (0, 0); the running sum starts at 0f like the Java's
+                d = K2S_ADD(d, t6[j]);                                         // (0, -1)
+                d = K2S_ADD(d, t6[j + 2]);                                     // (0, +1)
+                d = K2S_ADD(d, T[k][j]);                                       // (-1, 0)
+                d = K2S_ADD(d, T[k + 2][j]);                                   // (+1, 0)
+                dist[k][j] = d;
+            }
         }
-        st.b[c][0] = tl; st.b[c][5] = tr;
     }
-    K2SQuad q; q.x = dist[0]; q.y = dist[1]; q.z = dist[2]; q.w = dist[3];
-    k2s_st4(out_row + 4 * lane, q);
+    int so = k2s_slot(S0, rs_out);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        K2SQuad q; q.x = dist[k][0]; q.y = dist[k][1]; q.z = dist[k][2]; q.w = dist[k][3];
+        k2s_st4(outmap + so * K2S_PITCH + 4 * lane, q);
+        so = so + 1 == rs_out ? 0 : so + 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
 // W0: pass 0 (13-point double cross, Frame.java:44-55 crossList order) of stream row S: weights from the six maps, channel sums,
 // divide -> P0 ring.  Map order: 0 (0,1), 1 (1,0), 2 (1,1), 3 (1,-1), 4 (0,2), 5 (2,0); dist_{-d}(p) = map_d(p - d).
 // ------------------------------------------------------------------------------------------------------------------------
-K2S_FN void k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
+K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
     const K2Params &P = A.P;
     const K2SRow R = k2s_at(A, cur, S);
     const float *in = sm + K2S_OFF_GAB;
     float *ring = sm + K2S_OFF_P0;
     const int kind = R.valid ? k2s_row_kind(P, R.y, K2S_MARGIN_P0) : 1;
-    if (kind == 1) return;
-    if (kind == 2) { k2s_copy_behind(P, ring, K2S_RS_P0, R, S, lane); return; }
+    if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
     const float *d0 = sm + K2S_OFF_D0;
     const int s0 = k2s_slot(S, K2S_RS_D0), s1 = k2s_slot(S - 1, K2S_RS_D0), s2 = k2s_slot(S - 2, K2S_RS_D0);
 #define K2S_MAP(m, s) k2s_ld4(d0 + ((m) * K2S_RS_D0 + (s)) * K2S_PITCH + 4 * lane)
@@ -446,7 +459,7 @@ K2S_FN void k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
     const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));                            // copied through (Frame.java:608-612); also NaN
     const float ss = P.sigma_scale[0];
-    float w[4][12], sumw[4];
+    float w[4][12], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         w[j][0] = k2s_wgt(v01[j], m[j], ss, is);                         // (0,-1) = -(0,1): map at (y, x-1)
@@ -465,6 +478,7 @@ K2S_FN void k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
 #pragma unroll
         for (int k = 0; k < 12; k++) s = K2S_ADD(s, w[j][k]);
         sumw[j] = s;
+        rsum[j] = K2S_RCP(s);
     }
     K2SQuad out[3];
 #pragma unroll
@@ -492,24 +506,24 @@ K2S_FN void k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
             s = K2S_ADD(s, K2S_MUL(r8[j + 4], w[j][9]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(e, j), w[j][10]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(a, j), w[j][11]));
-            o[j] = pass ? r8[j + 2] : K2S_DIV(s, sumw[j]);
+            o[j] = pass ? r8[j + 2] : K2S_DIVS(s, sumw[j], rsum[j]);
         }
         out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
     }
     k2s_emit(P, ring, K2S_RS_P0, K2S_MARGIN_P0, R, S, lane, out);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
 // W1: pass 1 (5-point cross) of stream row S from the two maps; input ring = P0 (epf_iters == 3) or GAB.  LAST: epf_iters == 1,
 // the row goes through the colour transform to HBM instead of the P1 ring.
 // ------------------------------------------------------------------------------------------------------------------------
-template <int RS_IN, bool LAST> K2S_FN void k2s_w1_row(const K2SArgs &A, float *sm, const float *in, K2SCursor &cur, int S, int lane) {
+template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *sm, const float *in, K2SCursor &cur, int S, int lane) {
     const K2Params &P = A.P;
     const K2SRow R = k2s_at(A, cur, S);
     float *ring = sm + K2S_OFF_P1;
     const int kind = R.valid ? k2s_row_kind(P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
-    if (kind == 1) return;
-    if (kind == 2) { if (!LAST) k2s_copy_behind(P, ring, K2S_RS_P1, R, S, lane); return; }
+    if (kind != 0) return kind;
     const float *d1 = sm + K2S_OFF_D1;
     const K2SQuad q01 = k2s_ld4(d1 + (0 * K2S_RS_D1 + k2s_slot(S, K2S_RS_D1)) * K2S_PITCH + 4 * lane);
     const K2SQuad q10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + k2s_slot(S, K2S_RS_D1)) * K2S_PITCH + 4 * lane);
@@ -519,7 +533,7 @@ template <int RS_IN, bool LAST> K2S_FN void k2s_w1_row(const K2SArgs &A, float *
     const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));
     const float ss = P.sigma_scale[1];
-    float w[4][4], sumw[4];
+    float w[4][4], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         w[j][0] = k2s_wgt(v01[j], m[j], ss, is);
@@ -527,6 +541,7 @@ template <int RS_IN, bool LAST> K2S_FN void k2s_w1_row(const K2SArgs &A, float *
         w[j][2] = k2s_wgt(k2s_get(p10, j), m[j], ss, is);
         w[j][3] = k2s_wgt(k2s_get(q10, j), m[j], ss, is);
         sumw[j] = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w[j][0]), w[j][1]), w[j][2]), w[j][3]);
+        rsum[j] = K2S_RCP(sumw[j]);
     }
     K2SQuad out[3];
 #pragma unroll
@@ -543,12 +558,13 @@ template <int RS_IN, bool LAST> K2S_FN void k2s_w1_row(const K2SArgs &A, float *
             s = K2S_ADD(s, K2S_MUL(r6[j + 2], w[j][1]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(b, j), w[j][2]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(d, j), w[j][3]));
-            o[j] = pass ? r6[j + 1] : K2S_DIV(s, sumw[j]);
+            o[j] = pass ? r6[j + 1] : K2S_DIVS(s, sumw[j], rsum[j]);
         }
         out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
     }
     if (LAST) k2s_final(A, R, lane, out);
     else k2s_emit(P, ring, K2S_RS_P1, K2S_MARGIN_P1, R, S, lane, out);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -596,6 +612,7 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
         const float w0 = k2s_wgt(h[j], m[j], ss, is), w1 = k2s_wgt(h[j + 1], m[j], ss, is);
         const float w2 = k2s_wgt(vu[j], m[j], ss, is), w3 = k2s_wgt(vd[j], m[j], ss, is);
         const float sumw = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w0), w1), w2), w3);
+        const float rsum = K2S_RCP(sumw);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             float s = r6[c][j + 1];
@@ -603,7 +620,7 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
             s = K2S_ADD(s, K2S_MUL(r6[c][j + 2], w1));
             s = K2S_ADD(s, K2S_MUL(up[c][j], w2));
             s = K2S_ADD(s, K2S_MUL(dn[c][j], w3));
-            o[c][j] = pass ? r6[c][j + 1] : K2S_DIV(s, sumw);
+            o[c][j] = pass ? r6[c][j + 1] : K2S_DIVS(s, sumw, rsum);
         }
     }
     K2SQuad out[3];
@@ -613,8 +630,7 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// the tick loops of the roles.  n_ticks is the same for every warp; each role's loop carries its own rolling state, so the
-// kernel's register count is the maximum over the roles, not their sum.
+// the tick loop: every stage advances by one band, one stage after the other
 // ------------------------------------------------------------------------------------------------------------------------
 K2S_FN int k2s_total_rows(const K2SArgs &A) {
     const int cta = k2s_cta(), g = k2s_grid();
@@ -622,79 +638,47 @@ K2S_FN int k2s_total_rows(const K2SArgs &A) {
     return mine * A.ir;
 }
 
-template <int GAB, int ITERS>
-K2S_FN void k2s_role_g(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int n_ticks, int total, int lane) {
-    using Cfg = K2SCfg<ITERS>;
-    K2SGabState st;
-    K2SCursor cur;
-    k2s_cursor_init(cur);
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int i = 0; i < 6; i++) { st.n[c][i] = 0.0f; st.r[c][i] = 0.0f; }
-    for (int t = 0; t < n_ticks; t++) {
-        // rows [8t, 8t+8) of the stream -> RAW ring, two 4-row boxes per plane; the slots were last read in tick t-1
-        if (8 * t < total) {
-#ifdef K2S_HOST_EMU
-            if (lane == 0)
-                for (int h = 0; h < 2; h++) {
-                    const K2SRow R = k2s_locate(A, 8 * t + 4 * h);
-                    const int ty = R.z * A.P.rows + R.y + A.tma_row0, slot = k2s_slot(8 * t + 4 * h, K2S_RS_RAW);
-                    k2s_tma_box(sm + K2S_OFF_RAW + (0 * K2S_RS_RAW + slot) * K2S_PITCH, t0, R.x0 - K2S_HALO, ty);
-                    k2s_tma_box(sm + K2S_OFF_RAW + (1 * K2S_RS_RAW + slot) * K2S_PITCH, t1, R.x0 - K2S_HALO, ty);
-                    k2s_tma_box(sm + K2S_OFF_RAW + (2 * K2S_RS_RAW + slot) * K2S_PITCH, t2, R.x0 - K2S_HALO, ty);
-                }
-#else
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of tick t-1 before async-proxy writes
-                uint64_t *bar = bars + (t & 1);
-                k2s_mbar_expect_tx(bar, 6 * 4 * K2S_PITCH * 4);
-                for (int h = 0; h < 2; h++) {
-                    const K2SRow R = k2s_locate(A, 8 * t + 4 * h);
-                    const int ty = R.z * A.P.rows + R.y + A.tma_row0, slot = k2s_slot(8 * t + 4 * h, K2S_RS_RAW);
-                    k2s_tma_box_async(sm + K2S_OFF_RAW + (0 * K2S_RS_RAW + slot) * K2S_PITCH, t0, R.x0 - K2S_HALO, ty, bar);
-                    k2s_tma_box_async(sm + K2S_OFF_RAW + (1 * K2S_RS_RAW + slot) * K2S_PITCH, t1, R.x0 - K2S_HALO, ty, bar);
-                    k2s_tma_box_async(sm + K2S_OFF_RAW + (2 * K2S_RS_RAW + slot) * K2S_PITCH, t2, R.x0 - K2S_HALO, ty, bar);
-                }
-            }
-#endif
-        }
+// rows [16t, 16t + 16) of the stream -> RAW ring: four 4-row boxes per plane (an item is a multiple of 8 rows, a box never straddles
+// two).  One thread issues; the slots were last read by G in tick t - 1, which a CTA barrier separates from this call.
+K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int t, int total) {
+    int boxes = (total - K2S_BAND * t + 3) >> 2;
+    if (boxes <= 0) return;
+    if (boxes > K2S_BAND / 4) boxes = K2S_BAND / 4;
 #ifndef K2S_HOST_EMU
-        // the rows this tick reads arrived with the loads of tick t-1
-        if (t >= 1 && 8 * (t - 1) < total) k2s_mbar_wait(bars + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of tick t - 1 before async-proxy writes
+    uint64_t *bar = bars + (t & 1);
+    k2s_mbar_expect_tx(bar, boxes * 3 * 4 * K2S_PITCH * 4);
 #endif
 #pragma unroll 1
-        for (int r = 0; r < K2S_BAND; r++) {
-            const int S = 8 * t + Cfg::G + r;
-            // S == -1 primes the rolling window with stream row 0 (the row itself is not emitted)
-            if (S >= -1 && S < total) k2s_g_row<GAB>(A, sm, st, cur, S, lane);
-        }
+    for (int h = 0; h < boxes; h++) {
+        const int S = K2S_BAND * t + 4 * h;
+        const K2SRow R = k2s_locate(A, S);
+        const int ty = R.z * A.P.rows + R.y + A.tma_row0, slot = k2s_slot(S, K2S_RS_RAW);
+        float *dst = sm + K2S_OFF_RAW + slot * K2S_PITCH;
+#ifdef K2S_HOST_EMU
+        k2s_tma_box(dst, t0, R.x0 - K2S_HALO, ty);
+        k2s_tma_box(dst + K2S_RS_RAW * K2S_PITCH, t1, R.x0 - K2S_HALO, ty);
+        k2s_tma_box(dst + 2 * K2S_RS_RAW * K2S_PITCH, t2, R.x0 - K2S_HALO, ty);
+#else
+        k2s_tma_box_async(dst, t0, R.x0 - K2S_HALO, ty, bar);
+        k2s_tma_box_async(dst + K2S_RS_RAW * K2S_PITCH, t1, R.x0 - K2S_HALO, ty, bar);
+        k2s_tma_box_async(dst + 2 * K2S_RS_RAW * K2S_PITCH, t2, R.x0 - K2S_HALO, ty, bar);
+#endif
+    }
+}
+
+// End of a phase that writes a plane ring: CTA barrier, then the rows below the frame (kind 2) are copied from their mirror rows --
+// which another warp may have produced in this very phase -- and a second barrier publishes them.  Only the ticks that hold a frame's
+// last rows pay for the second one.
+K2S_FN void k2s_fixup(const K2SArgs &A, float *ring, int rs, K2SCursor &cur, int kind, int S, int lane) {
+    if (k2s_sync_or(kind == 2)) {
+        if (kind == 2) k2s_copy_behind(A.P, ring, rs, k2s_at(A, cur, S), S, lane);
         k2s_sync();
     }
 }
 
-K2S_FN void k2s_role_d(const K2SArgs &A, const float *in, int rs_in, float *outmap, int rs_out, int dy, int dx, int base, int n_ticks, int total, int lane) {
-    K2SDistState st;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) st.b[c][i] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { st.a[c][i] = 0.0f; st.i1[c][i] = 0.0f; st.i2[c][i] = 0.0f; }
-    }
-    const int plane_stride = rs_in * K2S_PITCH;
-    for (int t = 0; t < n_ticks; t++) {
-        int si = k2s_slot(8 * t + base + 1 + dy, rs_in), so = k2s_slot(8 * t + base, rs_out);     // ring slots advance with the rows
-#pragma unroll 1
-        for (int r = 0; r < K2S_BAND; r++) {
-            const int S = 8 * t + base + r;
-            // steps -3 .. -1 prime the rolling rows (row r is loaded at step r - 1 - dy); what they store lands in ring slots nobody has used yet
-            if (S >= -3 && S < total) k2s_d_row(A.P, in + si * K2S_PITCH, plane_stride, outmap + so * K2S_PITCH, dy, dx, st, lane);
-            si = si + 1 == rs_in ? 0 : si + 1;
-            so = so + 1 == rs_out ? 0 : so + 1;
-        }
-        k2s_sync();
-    }
+template <int DY, int DX> K2S_FN void k2s_d_task(const K2SArgs &A, const float *in, int rs_in, float *outmap, int rs_out, int S0, int total, int lane) {
+    if (S0 + 1 >= 0 && S0 < total) k2s_d_pair<DY, DX>(A.P, in, rs_in, outmap, rs_out, S0, lane);
 }
 
 template <int GAB, int ITERS>
@@ -711,80 +695,72 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
     }
     __syncthreads();
 #endif
-    float *gab = sm + K2S_OFF_GAB, *p0 = sm + K2S_OFF_P0, *d0 = sm + K2S_OFF_D0, *d1 = sm + K2S_OFF_D1;
+    float *gab = sm + K2S_OFF_GAB, *p0 = sm + K2S_OFF_P0, *p1 = sm + K2S_OFF_P1, *d0 = sm + K2S_OFF_D0, *d1 = sm + K2S_OFF_D1;
     const float *in1 = ITERS == 3 ? p0 : gab;                 // what pass 1 reads
+    constexpr int RS1 = ITERS == 3 ? K2S_RS_P0 : K2S_RS_GAB;
     K2SCursor cur;
     k2s_cursor_init(cur);
-    constexpr int RS1 = ITERS == 3 ? K2S_RS_P0 : K2S_RS_GAB;
-    // role of each warp.  Warp w issues on scheduler w % 4; heavy and light roles are interleaved so the four schedulers carry about
-    // the same number of instructions per tick (DESIGN.md has the budget).
-    if (ITERS == 3) {
-        //  warp:  0  1  2  3 | 4  5  6  7 | 8  9  10 11 | 12 13 14 15 | 16 17
-        //  role:  W0 W0 W0 W0| D0 D0 D0 D0| P2 P2 W1 W1 | D0 D0 P2 G  | D1 D1
-        if (warp < 4) {
-            for (int t = 0; t < n_ticks; t++) {
+    if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, 0, total);
+#ifdef K2S_HOST_EMU
+    k2s_sync();
+#endif
 #pragma unroll 1
-                for (int r = 0; r < 2; r++) {
-                    const int S = 8 * t + Cfg::W0 + 2 * warp + r;
-                    if (S >= 0 && S < total) k2s_w0_row(A, sm, cur, S, lane);
-                }
-                k2s_sync();
-            }
-        } else if ((warp >= 4 && warp < 8) || warp == 12 || warp == 13 || warp >= 16) {
-            // distance roles: pass 0 offsets (0,1) (1,0) (1,1) (1,-1) (0,2) (2,0) on warps 4-7, 12, 13; pass 1 offsets (0,1) (1,0) on warps 16, 17
-            const bool p1 = warp >= 16;
-            const int m = p1 ? warp - 16 : (warp < 8 ? warp - 4 : warp - 8);          // map index
-            const int dy = p1 ? m : (m == 0 || m == 4 ? 0 : (m == 5 ? 2 : 1));
-            const int dx = p1 ? 1 - m : (m == 0 ? 1 : m == 2 ? 1 : m == 3 ? -1 : m == 4 ? 2 : 0);
-            k2s_role_d(A, p1 ? in1 : gab, p1 ? RS1 : K2S_RS_GAB, p1 ? d1 + m * K2S_RS_D1 * K2S_PITCH : d0 + m * K2S_RS_D0 * K2S_PITCH,
-                       p1 ? K2S_RS_D1 : K2S_RS_D0, dy, dx, p1 ? Cfg::D1 : Cfg::D0, n_ticks, total, lane);
+    for (int t = 0; t < n_ticks; t++) {
+        const int S16 = K2S_BAND * t;
+        // ---- G ----
+#ifndef K2S_HOST_EMU
+        if (S16 < total) k2s_mbar_wait(bars + (t & 1), (t >> 1) & 1);
+#endif
+        {
+            const int S = S16 + Cfg::G + warp;
+            const int kind = (S >= 0 && S < total) ? k2s_g_row<GAB>(A, sm, cur, S, lane) : 1;
+            k2s_fixup(A, gab, K2S_RS_GAB, cur, kind, S, lane);
         }
-        else if (warp == 8 || warp == 9 || warp == 14) {
-            const int first = warp == 8 ? 0 : warp == 9 ? 3 : 6, count = warp == 14 ? 2 : 3;
-            for (int t = 0; t < n_ticks; t++) {
-#pragma unroll 1
-                for (int r = 0; r < count; r++) {
-                    const int S = 8 * t + Cfg::P2 + first + r;
-                    if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
+        if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, t + 1, total);     // lands while the other stages run
+        if (ITERS == 3) {
+            // ---- D0: 6 maps x 8 row pairs = 48 tasks, three per warp; a warp's three tasks are three different maps ----
+            {
+                const int S0 = S16 + Cfg::D0 + 2 * (warp & 7);
+                float *m0 = d0, *m1 = d0 + K2S_RS_D0 * K2S_PITCH;
+                if (warp < 8) {
+                    k2s_d_task<0, 1>(A, gab, K2S_RS_GAB, m0, K2S_RS_D0, S0, total, lane);
+                    k2s_d_task<1, 1>(A, gab, K2S_RS_GAB, m0 + 2 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
+                    k2s_d_task<0, 2>(A, gab, K2S_RS_GAB, m0 + 4 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
+                } else {
+                    k2s_d_task<1, 0>(A, gab, K2S_RS_GAB, m1, K2S_RS_D0, S0, total, lane);
+                    k2s_d_task<1, -1>(A, gab, K2S_RS_GAB, m1 + 2 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
+                    k2s_d_task<2, 0>(A, gab, K2S_RS_GAB, m1 + 4 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
                 }
-                k2s_sync();
             }
-        } else if (warp == 10 || warp == 11) {
-            for (int t = 0; t < n_ticks; t++) {
-#pragma unroll 1
-                for (int r = 0; r < 4; r++) {
-                    const int S = 8 * t + Cfg::W1 + 4 * (warp - 10) + r;
-                    if (S >= 0 && S < total) k2s_w1_row<RS1, false>(A, sm, in1, cur, S, lane);
-                }
-                k2s_sync();
+            k2s_sync();
+            // ---- W0 ----
+            {
+                const int S = S16 + Cfg::W0 + warp;
+                const int kind = (S >= 0 && S < total) ? k2s_w0_row(A, sm, cur, S, lane) : 1;
+                k2s_fixup(A, p0, K2S_RS_P0, cur, kind, S, lane);
             }
-        } else k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);      // warp 15
-    } else {
-        //  warp:  0  1  2  3 | 4  5  6  7 | 8  9  10        (epf_iters 2: W1 x4 then P2 x4;  epf_iters 1: W1 x8, the last stage)
-        //  role:  W1 W1 W1 W1| P2 P2 P2 P2| D1 D1 G
-        if (warp < 8 && (ITERS == 1 || warp < 4)) {
-            constexpr int per = ITERS == 1 ? 1 : 2;
-            for (int t = 0; t < n_ticks; t++) {
-#pragma unroll 1
-                for (int r = 0; r < per; r++) {
-                    const int S = 8 * t + Cfg::W1 + per * warp + r;
-                    if (S >= 0 && S < total) k2s_w1_row<RS1, ITERS == 1>(A, sm, in1, cur, S, lane);
-                }
-                k2s_sync();
-            }
-        } else if (warp < 8) {
-            for (int t = 0; t < n_ticks; t++) {
-#pragma unroll 1
-                for (int r = 0; r < 2; r++) {
-                    const int S = 8 * t + Cfg::P2 + 2 * (warp - 4) + r;
-                    if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
-                }
-                k2s_sync();
-            }
-        } else if (warp == 8 || warp == 9) {
-            const int m = warp - 8;
-            k2s_role_d(A, in1, RS1, d1 + m * K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, m, 1 - m, Cfg::D1, n_ticks, total, lane);
-        } else k2s_role_g<GAB, ITERS>(A, sm, bars, t0, t1, t2, n_ticks, total, lane);
+        }
+        // ---- D1: 2 maps x 8 row pairs ----
+        {
+            const int S0 = S16 + Cfg::D1 + 2 * (warp & 7);
+            if (warp < 8) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
+            else k2s_d_task<1, 0>(A, in1, RS1, d1 + K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, S0, total, lane);
+        }
+        k2s_sync();
+        // ---- W1 ----
+        {
+            const int S = S16 + Cfg::W1 + warp;
+            const int kind = (S >= 0 && S < total) ? k2s_w1_row<RS1, ITERS == 1>(A, sm, in1, cur, S, lane) : 1;
+            if (ITERS > 1) k2s_fixup(A, p1, K2S_RS_P1, cur, kind, S, lane);
+        }
+        // ---- P2 ----
+        if (ITERS > 1) {
+            const int S = S16 + Cfg::P2 + warp;
+            if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
+        }
+        // epf_iters > 1: no barrier here -- G of tick t + 1 reads the RAW ring and writes GAB slots whose last readers ran before the
+        // barriers above.  epf_iters == 1: W1 has just read the GAB ring, and G is about to write it.
+        if (ITERS == 1) k2s_sync();
     }
 }
 
@@ -814,7 +790,7 @@ static inline void k2s_plan(int W, int rows, int n_frames, int n_cta, K2SArgs &A
 
 #ifndef K2S_HOST_EMU
 template <int GAB, int ITERS>
-__global__ void __launch_bounds__(32 * K2SCfg<ITERS>::NWARPS, 1)
+__global__ void __launch_bounds__(32 * K2S_NWARPS, 1)
 k2_stream(const __grid_constant__ K2SArgs A, const __grid_constant__ CUtensorMap t0, const __grid_constant__ CUtensorMap t1,
           const __grid_constant__ CUtensorMap t2) {
     extern __shared__ __align__(128) float k2s_smem[];
@@ -881,7 +857,7 @@ static inline int k2_stream_launch(const K2Params &K, const float *inv_sigma, cu
             return -1;
     }
     const int grid = A.n_items < sms ? A.n_items : sms;
-#define K2S_GO(G, I) k2_stream<G, I><<<grid, 32 * K2SCfg<I>::NWARPS, K2S_BYTES, st>>>(A, tm[0], tm[1], tm[2])
+#define K2S_GO(G, I) k2_stream<G, I><<<grid, 32 * K2S_NWARPS, K2S_BYTES, st>>>(A, tm[0], tm[1], tm[2])
     switch ((K.gab ? 4 : 0) + K.iters) {
     case 5: K2S_GO(1, 1); break;
     case 6: K2S_GO(1, 2); break;

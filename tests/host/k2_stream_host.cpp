@@ -17,6 +17,8 @@ struct Emu {
     pthread_barrier_t cta_bar;
     std::vector<pthread_barrier_t> warp_bar;
     std::vector<float> xch;
+    int any[2] = {0, 0};
+    std::vector<int> any_phase;
 } g;
 thread_local int t_tid = 0;
 }  // namespace
@@ -33,6 +35,16 @@ float k2s_emu_shfl(float v, int src_lane) {
     return r;
 }
 void k2s_emu_sync() { pthread_barrier_wait(&g.cta_bar); }
+int k2s_emu_sync_or(int pred) {
+    if (pred) __atomic_store_n(&g.any[g.any_phase[t_tid] & 1], 1, __ATOMIC_RELAXED);
+    pthread_barrier_wait(&g.cta_bar);
+    const int r = __atomic_load_n(&g.any[g.any_phase[t_tid] & 1], __ATOMIC_RELAXED);
+    pthread_barrier_wait(&g.cta_bar);
+    // the flag of this parity is cleared by thread 0 only after everybody has read it; the next sync_or uses the other flag
+    if (t_tid == 0) __atomic_store_n(&g.any[g.any_phase[t_tid] & 1], 0, __ATOMIC_RELAXED);
+    g.any_phase[t_tid]++;
+    return r;
+}
 
 namespace {
 struct Job {
@@ -120,10 +132,12 @@ extern "C" int k2s_host_run(const jxlb200_frame_params *p, const jxlb200_slab *s
         tm[c].rows = K.rows * n_frames + (K.has_top ? JXLB200_HALO_ROWS : 0) + (K.has_bottom ? JXLB200_HALO_ROWS : 0);
         tm[c].pitch = in_pitch;
     }
-    const int nw = p->epf_iters == 3 ? K2SCfg<3>::NWARPS : K2SCfg<1>::NWARPS;
+    const int nw = K2S_NWARPS;
     g.n_warps = nw;
     g.grid = A.n_items < grid ? A.n_items : grid;
     g.xch.assign((size_t)nw * 32, 0.0f);
+    g.any_phase.assign((size_t)nw * 32, 0);
+    g.any[0] = g.any[1] = 0;
     g.warp_bar.resize(nw);
     std::vector<float> sm(K2S_FLOATS + 16);
     for (int cta = 0; cta < g.grid; cta++) {

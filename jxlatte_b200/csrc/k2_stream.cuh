@@ -47,6 +47,7 @@
 #define K2S_MUL(a, b) ((a) * (b))
 #define K2S_RCP(b) (0.0f)
 #define K2S_DIVS(a, b, r) ((a) / (b))
+
 #define K2S_LDG(p) (*(p))
 #else
 #include <cuda.h>
@@ -57,6 +58,7 @@
 #define K2S_MUL(a, b) __fmul_rn((a), (b))
 #define K2S_RCP(b) kx_rcp_refined(b)
 #define K2S_DIVS(a, b, r) kx_div_shared((a), (b), (r))
+
 #define K2S_LDG(p) __ldg(p)
 #endif
 
@@ -68,16 +70,24 @@
 #define K2S_TW 112            /* useful columns of a column strip */
 #define K2S_HALO 8            /* halo columns each side and halo rows each side of an item (7 used: 1 + 3 + 2 + 1) */
 #define K2S_PITCH 128         /* floats per ring row: 32 lanes x 4 */
-#define K2S_BAND 16           /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase */
-#define K2S_NWARPS 16
-// Ring sizes in rows.  Within a tick the writer of a ring runs before its readers; a ring must hold the rows its readers still need
-// when the writer's next band lands on top of the oldest slots (worked out row by row in DESIGN.md).
-#define K2S_RS_RAW 20
-#define K2S_RS_GAB 24
-#define K2S_RS_P0 20
-#define K2S_RS_P1 18
-#define K2S_RS_D0 18
-#define K2S_RS_D1 17
+#ifndef K2S_BAND
+#define K2S_BAND 8            /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase.  8: two CTAs per SM,
+                                 one computes while the other sits at a barrier; 16: one CTA per SM */
+#endif
+#define K2S_NWARPS K2S_BAND
+#define K2S_CTAS_PER_SM (K2S_BAND == 8 ? 2 : 1)
+// Ring sizes in rows.  Within a tick the writer of a ring (first row of its band: 16t + bw) runs before its readers (16t + br, reading
+// up to `a` rows above their own); when the writer's band lands, the readers of the same tick still need everything from row
+// 16t + br - a on, so a ring holds BAND + bw - br + a rows:
+//   GAB: G -2, W0 -6 reads 2 above -> BAND + 6      D0 maps: D0 -6, W0 -6 reads 2 above -> BAND + 2
+//   P0:  W0 -6, D1 / W1 -8 read 1 above -> BAND + 3  D1 maps: D1 -8, W1 -8 reads 1 above -> BAND + 1
+//   P1:  W1 -8, P2 -9 reads 1 above -> BAND + 2      RAW: next band's loads are issued after G; G -2 reads 1 above -> BAND + 3, in boxes of 4
+#define K2S_RS_RAW ((K2S_BAND + 3 + 3) & ~3)
+#define K2S_RS_GAB (K2S_BAND + 6)
+#define K2S_RS_P0 (K2S_BAND + 3)
+#define K2S_RS_P1 (K2S_BAND + 2)
+#define K2S_RS_D0 (K2S_BAND + 2)
+#define K2S_RS_D1 (K2S_BAND + 1)
 #define K2S_OFF_RAW 0
 #define K2S_OFF_GAB (K2S_OFF_RAW + 3 * K2S_RS_RAW * K2S_PITCH)
 #define K2S_OFF_P0 (K2S_OFF_GAB + 3 * K2S_RS_GAB * K2S_PITCH)
@@ -105,7 +115,7 @@ struct K2SArgs {
     int tma_row0;               // tensor-map row of frame row 0 (8 when the slab has rows above it)
 };
 
-// In tick t a stage processes stream rows [16t + base, 16t + base + 16); the TMA loads of tick t bring rows [16t, 16t + 16).
+// In tick t a stage processes stream rows [BAND t + base, BAND t + base + BAND); the TMA loads of tick t bring rows [BAND t, BAND t + BAND).
 // A stage trails its producer by the rows below its own that it reads, and by one more where a row ABOVE the frame is involved: such a
 // row exists only once its mirror source has been produced (row -k is written together with row k-1).  D0 evaluates map rows down to
 // y = -2 (pass 0 at row 0 uses dist_(2,0) at row -2), which read GAB rows down to -3, written with GAB row 2 = y + 4.
@@ -307,6 +317,22 @@ K2S_FN void k2s_final(const K2SArgs &A, const K2SRow &R, int lane, K2SQuad q[3])
 K2S_FN float k2s_wgt(float dist, float m, float ss, float is) {
     return fmaxf(K2S_SUB(1.0f, K2S_MUL(K2S_MUL(K2S_MUL(dist, m), ss), is)), 0.0f);
 }
+// the four divides of a row quad, a[j] / b[j] with r[j] = K2S_RCP(b[j]): one range test for the four numerators (kx_div_shared's
+// fast path is exact inside it, k2_exact.cuh) instead of one test, branch and reconvergence point per divide
+K2S_FN void k2s_div4(const float a[4], const float b[4], const float r[4], float o[4]) {
+#ifdef K2S_HOST_EMU
+    for (int j = 0; j < 4; j++) o[j] = a[j] / b[j];
+#else
+    const bool ok = kx_div_fast_ok(a[0]) & kx_div_fast_ok(a[1]) & kx_div_fast_ok(a[2]) & kx_div_fast_ok(a[3]);
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = kx_div_fast(a[j], b[j], r[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = __fdiv_rn(a[j], b[j]);
+    }
+#endif
+}
 // 1/sigma of the lane's block in row y, and the border multipliers of its four pixels
 K2S_FN float k2s_sigma(const K2SArgs &A, const K2SRow &R, int lane, float m[4]) {
     const K2Params &P = A.P;
@@ -387,13 +413,15 @@ template <int DY, int DX> K2S_FN void k2s_d_pair(const K2Params &P, const float 
     // the channel loop stays rolled (trip count read from a kernel argument, or the compiler unrolls it whatever the pragma says): the
     // D0 phase runs six instances of this body at once, and unrolled they are two instruction caches' worth of code
     const int nch = K2S_ROLLED_TRIPS(P);
+#pragma unroll
+    for (int i = 0; i < 4 + DY; i++) slot[i] = slot[i] * K2S_PITCH + 4 * lane;       // float offset of the lane's quad in the row
 #pragma unroll 1
     for (int c = 0; c < nch; c++) {
-        const float *pl = in + c * rs_in * K2S_PITCH + 4 * lane;
+        const float *pl = in + c * rs_in * K2S_PITCH;
         float I[4 + DY][4];
 #pragma unroll
         for (int i = 0; i < 4 + DY; i++) {
-            const K2SQuad q = k2s_ld4(pl + slot[i] * K2S_PITCH);
+            const K2SQuad q = k2s_ld4(pl + slot[i]);
             I[i][0] = q.x; I[i][1] = q.y; I[i][2] = q.z; I[i][3] = q.w;
         }
         const float s = P.ch_scale[c];
@@ -490,7 +518,7 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
         const float b6[6] = {k2s_up(b.w), b.x, b.y, b.z, b.w, k2s_dn(b.x)};
         const float d6[6] = {k2s_up(d.w), d.x, d.y, d.z, d.w, k2s_dn(d.x)};
         const float r8[8] = {k2s_up(r.z), k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x), k2s_dn(r.y)};
-        float o[4];
+        float o[4], sv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = r8[j + 2];                                          // 0 + I * 1
@@ -506,8 +534,10 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
             s = K2S_ADD(s, K2S_MUL(r8[j + 4], w[j][9]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(e, j), w[j][10]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(a, j), w[j][11]));
-            o[j] = pass ? r8[j + 2] : K2S_DIVS(s, sumw[j], rsum[j]);
+            sv[j] = s;
         }
+        k2s_div4(sv, sumw, rsum, o);
+        if (pass) { o[0] = r8[2]; o[1] = r8[3]; o[2] = r8[4]; o[3] = r8[5]; }
         out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
     }
     k2s_emit(P, ring, K2S_RS_P0, K2S_MARGIN_P0, R, S, lane, out);
@@ -550,7 +580,7 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
         const K2SQuad b = k2s_ld4(pl + k2s_slot(S - 1, RS_IN) * K2S_PITCH), r = k2s_ld4(pl + k2s_slot(S, RS_IN) * K2S_PITCH);
         const K2SQuad d = k2s_ld4(pl + k2s_slot(S + 1, RS_IN) * K2S_PITCH);
         const float r6[6] = {k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x)};
-        float o[4];
+        float o[4], sv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = r6[j + 1];
@@ -558,8 +588,10 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
             s = K2S_ADD(s, K2S_MUL(r6[j + 2], w[j][1]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(b, j), w[j][2]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(d, j), w[j][3]));
-            o[j] = pass ? r6[j + 1] : K2S_DIVS(s, sumw[j], rsum[j]);
+            sv[j] = s;
         }
+        k2s_div4(sv, sumw, rsum, o);
+        if (pass) { o[0] = r6[1]; o[1] = r6[2]; o[2] = r6[3]; o[3] = r6[4]; }
         out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
     }
     if (LAST) k2s_final(A, R, lane, out);
@@ -606,13 +638,13 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
     const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));
     const float ss = P.sigma_scale[2];
-    float o[3][4];
+    float o[3][4], sv[3][4], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const float w0 = k2s_wgt(h[j], m[j], ss, is), w1 = k2s_wgt(h[j + 1], m[j], ss, is);
         const float w2 = k2s_wgt(vu[j], m[j], ss, is), w3 = k2s_wgt(vd[j], m[j], ss, is);
-        const float sumw = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w0), w1), w2), w3);
-        const float rsum = K2S_RCP(sumw);
+        sumw[j] = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w0), w1), w2), w3);
+        rsum[j] = K2S_RCP(sumw[j]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             float s = r6[c][j + 1];
@@ -620,8 +652,13 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
             s = K2S_ADD(s, K2S_MUL(r6[c][j + 2], w1));
             s = K2S_ADD(s, K2S_MUL(up[c][j], w2));
             s = K2S_ADD(s, K2S_MUL(dn[c][j], w3));
-            o[c][j] = pass ? r6[c][j + 1] : K2S_DIVS(s, sumw, rsum);
+            sv[c][j] = s;
         }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        k2s_div4(sv[c], sumw, rsum, o[c]);
+        if (pass) { o[c][0] = r6[c][1]; o[c][1] = r6[c][2]; o[c][2] = r6[c][3]; o[c][3] = r6[c][4]; }
     }
     K2SQuad out[3];
 #pragma unroll
@@ -640,7 +677,8 @@ K2S_FN int k2s_total_rows(const K2SArgs &A) {
 
 // rows [16t, 16t + 16) of the stream -> RAW ring: four 4-row boxes per plane (an item is a multiple of 8 rows, a box never straddles
 // two).  One thread issues; the slots were last read by G in tick t - 1, which a CTA barrier separates from this call.
-K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int t, int total) {
+K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int t, int total,
+                              K2SCursor &cur) {
     int boxes = (total - K2S_BAND * t + 3) >> 2;
     if (boxes <= 0) return;
     if (boxes > K2S_BAND / 4) boxes = K2S_BAND / 4;
@@ -652,7 +690,7 @@ K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_
 #pragma unroll 1
     for (int h = 0; h < boxes; h++) {
         const int S = K2S_BAND * t + 4 * h;
-        const K2SRow R = k2s_locate(A, S);
+        const K2SRow R = k2s_at(A, cur, S);       // the issuing thread's warp is on the phase's critical path: no divisions here
         const int ty = R.z * A.P.rows + R.y + A.tma_row0, slot = k2s_slot(S, K2S_RS_RAW);
         float *dst = sm + K2S_OFF_RAW + slot * K2S_PITCH;
 #ifdef K2S_HOST_EMU
@@ -700,7 +738,7 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
     constexpr int RS1 = ITERS == 3 ? K2S_RS_P0 : K2S_RS_GAB;
     K2SCursor cur;
     k2s_cursor_init(cur);
-    if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, 0, total);
+    if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, 0, total, cur);
 #ifdef K2S_HOST_EMU
     k2s_sync();
 #endif
@@ -716,13 +754,13 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             const int kind = (S >= 0 && S < total) ? k2s_g_row<GAB>(A, sm, cur, S, lane) : 1;
             k2s_fixup(A, gab, K2S_RS_GAB, cur, kind, S, lane);
         }
-        if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, t + 1, total);     // lands while the other stages run
+        if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, t + 1, total, cur);     // lands while the other stages run
         if (ITERS == 3) {
-            // ---- D0: 6 maps x 8 row pairs = 48 tasks, three per warp; a warp's three tasks are three different maps ----
+            // ---- D0: 6 maps x BAND / 2 row pairs, three tasks per warp; a warp's three tasks are three different maps ----
             {
-                const int S0 = S16 + Cfg::D0 + 2 * (warp & 7);
+                const int S0 = S16 + Cfg::D0 + 2 * (warp & (K2S_BAND / 2 - 1));
                 float *m0 = d0, *m1 = d0 + K2S_RS_D0 * K2S_PITCH;
-                if (warp < 8) {
+                if (warp < K2S_BAND / 2) {
                     k2s_d_task<0, 1>(A, gab, K2S_RS_GAB, m0, K2S_RS_D0, S0, total, lane);
                     k2s_d_task<1, 1>(A, gab, K2S_RS_GAB, m0 + 2 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
                     k2s_d_task<0, 2>(A, gab, K2S_RS_GAB, m0 + 4 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
@@ -740,10 +778,10 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
                 k2s_fixup(A, p0, K2S_RS_P0, cur, kind, S, lane);
             }
         }
-        // ---- D1: 2 maps x 8 row pairs ----
+        // ---- D1: 2 maps x BAND / 2 row pairs ----
         {
-            const int S0 = S16 + Cfg::D1 + 2 * (warp & 7);
-            if (warp < 8) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
+            const int S0 = S16 + Cfg::D1 + 2 * (warp & (K2S_BAND / 2 - 1));
+            if (warp < K2S_BAND / 2) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
             else k2s_d_task<1, 0>(A, in1, RS1, d1 + K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, S0, total, lane);
         }
         k2s_sync();
@@ -790,7 +828,7 @@ static inline void k2s_plan(int W, int rows, int n_frames, int n_cta, K2SArgs &A
 
 #ifndef K2S_HOST_EMU
 template <int GAB, int ITERS>
-__global__ void __launch_bounds__(32 * K2S_NWARPS, 1)
+__global__ void __launch_bounds__(32 * K2S_NWARPS, K2S_CTAS_PER_SM)
 k2_stream(const __grid_constant__ K2SArgs A, const __grid_constant__ CUtensorMap t0, const __grid_constant__ CUtensorMap t1,
           const __grid_constant__ CUtensorMap t2) {
     extern __shared__ __align__(128) float k2s_smem[];
@@ -843,7 +881,8 @@ static inline int k2_stream_launch(const K2Params &K, const float *inv_sigma, cu
     A.inv_sigma = inv_sigma;
     A.zpx = (long long)K.rows * K.in_pitch;
     A.zblk = (K.rows >> 3) * K.wb;
-    k2s_plan(K.W, K.rows, n_frames, sms, A);
+    const int n_cta = sms * K2S_CTAS_PER_SM;
+    k2s_plan(K.W, K.rows, n_frames, n_cta, A);
     A.tma_row0 = K.has_top ? JXLB200_HALO_ROWS : 0;
     const long long map_rows = (long long)K.rows * n_frames + (K.has_top ? JXLB200_HALO_ROWS : 0) + (K.has_bottom ? JXLB200_HALO_ROWS : 0);
     CUtensorMap tm[3];
@@ -856,7 +895,7 @@ static inline int k2_stream_launch(const K2Params &K, const float *inv_sigma, cu
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return -1;
     }
-    const int grid = A.n_items < sms ? A.n_items : sms;
+    const int grid = A.n_items < n_cta ? A.n_items : n_cta;
 #define K2S_GO(G, I) k2_stream<G, I><<<grid, 32 * K2S_NWARPS, K2S_BYTES, st>>>(A, tm[0], tm[1], tm[2])
     switch ((K.gab ? 4 : 0) + K.iters) {
     case 5: K2S_GO(1, 1); break;

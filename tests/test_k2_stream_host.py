@@ -18,10 +18,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HALO = 8
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["libk2stream_host.so", "libk2stream_host16.so"], ids=["band8", "band16"])
+def emu(request):
     subprocess.check_call(["make", "-C", os.path.join(HERE, "host")], stdout=subprocess.DEVNULL)
-    L = C.CDLL(os.path.join(HERE, "host", "libk2stream_host.so"))
+    L = C.CDLL(os.path.join(HERE, "host", request.param))
     L.k2s_host_run.restype = C.c_int
     L.k2s_host_run.argtypes = [C.POINTER(FrameParams), C.POINTER(Slab), C.c_int, C.POINTER(C.c_void_p), C.c_longlong,
                                C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]

@@ -350,7 +350,12 @@ def run_ours(args):
                            d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), xyb, W)
             rec.sync()
         peak, which = peaks()
-        dom = "k2_exact (fused Gaborish+EPF+colour, bit-exact)" if t2 >= t1 else "stage 1 (k1_small/medium/big: dequant+CfL+LLF+IDCT)"
+        # stage 2 of a frame this size with Gaborish on is the stream kernel (csrc/jxlb200.cu: stream_pays), else the tile kernel
+        k2_name = ("k2_stream (persistent, TMA-fed row rings: fused Gaborish+EPF+colour, bit-exact)" if (W * H >= 600000 and p.gab and iters >= 1)
+                   else "k2_exact (fused Gaborish+EPF+colour, bit-exact)")
+        if os.environ.get("JXLB200_STAGE2"):
+            k2_name = "stage 2 as selected by JXLB200_STAGE2=%s" % os.environ["JXLB200_STAGE2"]
+        dom = k2_name if t2 >= t1 else "stage 1 (k1_small/medium/big: dequant+CfL+LLF+IDCT)"
         bpp = BYTES_PER_PX_K2 if t2 >= t1 else BYTES_PER_PX
         ach = bpp * W * H / (max(t1, t2) / 1e3) / 1e9
         traffic = None

@@ -17,7 +17,7 @@ HALO_ROWS = 8
 OPT_STAGE2 = 1
 OPT_OVERLAP_ROWS = 2
 OPT_PIPE_ROWS, OPT_PIPE_FANOUT = 3, 4
-STAGE2_AUTO, STAGE2_STAGED, STAGE2_FUSED, STAGE2_PAIR, STAGE2_STREAM = 0, 1, 2, 3, 5
+STAGE2_AUTO, STAGE2_STAGED, STAGE2_FUSED, STAGE2_PAIR, STAGE2_STREAM, STAGE2_TILE = 0, 1, 2, 3, 5, 6
 
 
 class QmParams(C.Structure):

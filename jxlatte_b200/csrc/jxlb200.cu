@@ -16,9 +16,7 @@
 #include "k2_fused.cuh"
 #include "k2_exact.cuh"
 // measured-and-parked stage-2 variants: in the tree and tested (CPU emulator / opt-in builds), not in the default library
-#ifdef JXLB200_WITH_STREAM
-#include "k2_stream.cuh"     /* persistent warp-specialised stream: bit-exact, instruction-fetch-bound (profiles/r2_k2_stream_ncu.md) */
-#endif
+#include "k2_stream.cuh"     /* default stage 2: persistent CTAs streaming column strips through TMA-fed row rings, bit-exact */
 #ifdef JXLB200_WITH_PAIR
 #include "k2_pair.cuh"       /* packed FP32x2: bit-exact, measured slower (profiles/r1_k2_pair_ncu.md) */
 #endif
@@ -165,9 +163,7 @@ int upload_constants(jxlb200_ctx *ctx) {
     CUDA_TRY(ctx, (big_attr<128, 1>())); CUDA_TRY(ctx, (big_attr<256, 1>()));
     CUDA_TRY(ctx, k2_fused_init_all());
     CUDA_TRY(ctx, k2_exact_init_all());
-#ifdef JXLB200_WITH_STREAM
     CUDA_TRY(ctx, k2_stream_init_all());
-#endif
 #ifdef JXLB200_WITH_PAIR
     CUDA_TRY(ctx, k2_pair_init_all());
 #endif
@@ -415,14 +411,18 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                          ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-#ifdef JXLB200_WITH_STREAM
-    if (ctx->opt_stage2 == 5 && k2_stream_supported(K, n_frames) && k2_stream_launch(K, inv_sigma, st, n_frames, ctx->sms) == 0) {
+    // Two bit-exact fused kernels.  Default: the stream kernel where it is the faster one (Gaborish on, at least 0.6 MP: 8K frame, gab +
+    // EPF 3: 1.52 ms against 1.66 ms; without Gaborish its copy stage costs more than the tile kernel's halo, and a small frame does not
+    // fill 148 persistent CTAs -- tools/stage2_matrix.py, profiles/r2_stage2_matrix.md), else the tile kernel.  5 forces the stream
+    // kernel wherever the planes can take TMA (16-byte aligned bases and pitches, epf_iters >= 1), 6 forces the tile kernel.
+    const bool stream_pays = K.gab && (long long)K.W * K.rows * n_frames >= 600000ll;
+    if (((ctx->opt_stage2 == 0 && stream_pays) || ctx->opt_stage2 == 5) && k2_stream_supported(K, n_frames) &&
+        k2_stream_launch(K, inv_sigma, st, n_frames, ctx->sms) == 0) {
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
         return 0;
     }
-#endif
-    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 5) && k2_exact_supported(K)) {   // default: fused tile kernel, bit-exact
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 5 || ctx->opt_stage2 == 6) && k2_exact_supported(K)) {
 #ifdef JXLB200_WITH_PAIR
         if (ctx->opt_stage2 == 3) k2_pair_dispatch(K, inv_sigma, st, n_frames);      // two blocks per thread on packed FP32x2: same bits, measured slower
         else
@@ -621,12 +621,9 @@ int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return JXLB200_E_ARG;
-    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 5) {
+    if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 6) {
 #ifndef JXLB200_WITH_PAIR
         if (value == 3) return ctx->fail(JXLB200_E_UNSUPPORTED, "this library was built without k2_pair (-DJXLB200_WITH_PAIR)");
-#endif
-#ifndef JXLB200_WITH_STREAM
-        if (value == 5) return ctx->fail(JXLB200_E_UNSUPPORTED, "this library was built without k2_stream (-DJXLB200_WITH_STREAM)");
 #endif
         if (value == 4) return ctx->fail(JXLB200_E_ARG, "unknown option or value");
         ctx->opt_stage2 = value;
@@ -816,7 +813,7 @@ int32_t jxlb200_vardct_reconstruct_batch_dev(jxlb200_ctx *ctx, const jxlb200_fra
     if (rc) return rc;
     K2Params K;
     fill_k2(K, p, nullptr);
-    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 5) && k2_exact_supported(K)) {   // one launch over the whole stack
+    if ((ctx->opt_stage2 == 0 || ctx->opt_stage2 == 3 || ctx->opt_stage2 == 5 || ctx->opt_stage2 == 6) && k2_exact_supported(K)) {   // one launch over the whole stack
         const float *m3[3] = {mid[0], mid[1], mid[2]};
         return restore_dev(ctx, p, nullptr, m3, W, hf_mul, sharpness, out, n_frames);
     }

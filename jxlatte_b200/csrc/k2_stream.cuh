@@ -71,8 +71,9 @@
 #define K2S_HALO 8            /* halo columns each side and halo rows each side of an item (7 used: 1 + 3 + 2 + 1) */
 #define K2S_PITCH 128         /* floats per ring row: 32 lanes x 4 */
 #ifndef K2S_BAND
-#define K2S_BAND 8            /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase.  8: two CTAs per SM,
-                                 one computes while the other sits at a barrier; 16: one CTA per SM */
+#define K2S_BAND 16           /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase.  16: one CTA per SM
+                                 (8K frame, stage 2: 1.52 ms); 8: two CTAs of 8 warps per SM, one computes while the other sits at a
+                                 barrier (1.55 ms: the barriers are not what limits it) */
 #endif
 #define K2S_NWARPS K2S_BAND
 #define K2S_CTAS_PER_SM (K2S_BAND == 8 ? 2 : 1)
@@ -202,6 +203,9 @@ K2S_FN void k2s_tma_box_async(float *dst, const K2STmap *m, int x, int y, uint64
 
 K2S_FN float k2s_get(const K2SQuad &q, int j) { return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w; }
 K2S_FN int k2s_slot(int S, int rs) { int s = S % rs; return s < 0 ? s + rs : s; }
+// the neighbouring slots of one that is known: a compare and a select instead of a division by a constant
+K2S_FN int k2s_next(int s, int rs) { return s + 1 == rs ? 0 : s + 1; }
+K2S_FN int k2s_prev(int s, int rs) { return s == 0 ? rs - 1 : s - 1; }
 
 // ------------------------------------------------------------------------------------------------------------------------
 // where a stream row lies: item -> (frame of the stack, column strip, chunk) -> frame row / first column
@@ -405,7 +409,7 @@ template <int DY, int DX> K2S_FN void k2s_d_pair(const K2Params &P, const float 
     int slot[4 + DY];
     slot[0] = k2s_slot(S0 - 1, rs_in);
 #pragma unroll
-    for (int i = 1; i < 4 + DY; i++) slot[i] = slot[i - 1] + 1 == rs_in ? 0 : slot[i - 1] + 1;
+    for (int i = 1; i < 4 + DY; i++) slot[i] = k2s_next(slot[i - 1], rs_in);
 #pragma unroll
     for (int k = 0; k < 2; k++)
 #pragma unroll
@@ -473,7 +477,9 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
     const int kind = R.valid ? k2s_row_kind(P, R.y, K2S_MARGIN_P0) : 1;
     if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
     const float *d0 = sm + K2S_OFF_D0;
-    const int s0 = k2s_slot(S, K2S_RS_D0), s1 = k2s_slot(S - 1, K2S_RS_D0), s2 = k2s_slot(S - 2, K2S_RS_D0);
+    const int s0 = k2s_slot(S, K2S_RS_D0), s1 = k2s_prev(s0, K2S_RS_D0), s2 = k2s_prev(s1, K2S_RS_D0);
+    const int g2 = k2s_slot(S, K2S_RS_GAB), g1 = k2s_prev(g2, K2S_RS_GAB), g0 = k2s_prev(g1, K2S_RS_GAB), g3 = k2s_next(g2, K2S_RS_GAB),
+              g4 = k2s_next(g3, K2S_RS_GAB);
 #define K2S_MAP(m, s) k2s_ld4(d0 + ((m) * K2S_RS_D0 + (s)) * K2S_PITCH + 4 * lane)
     const K2SQuad q01 = K2S_MAP(0, s0), q10 = K2S_MAP(1, s0), q11 = K2S_MAP(2, s0), q1m = K2S_MAP(3, s0), q02 = K2S_MAP(4, s0), q20 = K2S_MAP(5, s0);
     const K2SQuad p10 = K2S_MAP(1, s1), p11 = K2S_MAP(2, s1), p1m = K2S_MAP(3, s1), p20 = K2S_MAP(5, s2);
@@ -512,9 +518,9 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *pl = in + c * K2S_RS_GAB * K2S_PITCH + 4 * lane;
-        const K2SQuad a = k2s_ld4(pl + k2s_slot(S - 2, K2S_RS_GAB) * K2S_PITCH), b = k2s_ld4(pl + k2s_slot(S - 1, K2S_RS_GAB) * K2S_PITCH);
-        const K2SQuad r = k2s_ld4(pl + k2s_slot(S, K2S_RS_GAB) * K2S_PITCH);
-        const K2SQuad d = k2s_ld4(pl + k2s_slot(S + 1, K2S_RS_GAB) * K2S_PITCH), e = k2s_ld4(pl + k2s_slot(S + 2, K2S_RS_GAB) * K2S_PITCH);
+        const K2SQuad a = k2s_ld4(pl + g0 * K2S_PITCH), b = k2s_ld4(pl + g1 * K2S_PITCH);
+        const K2SQuad r = k2s_ld4(pl + g2 * K2S_PITCH);
+        const K2SQuad d = k2s_ld4(pl + g3 * K2S_PITCH), e = k2s_ld4(pl + g4 * K2S_PITCH);
         const float b6[6] = {k2s_up(b.w), b.x, b.y, b.z, b.w, k2s_dn(b.x)};
         const float d6[6] = {k2s_up(d.w), d.x, d.y, d.z, d.w, k2s_dn(d.x)};
         const float r8[8] = {k2s_up(r.z), k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x), k2s_dn(r.y)};
@@ -555,9 +561,11 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
     const int kind = R.valid ? k2s_row_kind(P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
     if (kind != 0) return kind;
     const float *d1 = sm + K2S_OFF_D1;
-    const K2SQuad q01 = k2s_ld4(d1 + (0 * K2S_RS_D1 + k2s_slot(S, K2S_RS_D1)) * K2S_PITCH + 4 * lane);
-    const K2SQuad q10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + k2s_slot(S, K2S_RS_D1)) * K2S_PITCH + 4 * lane);
-    const K2SQuad p10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + k2s_slot(S - 1, K2S_RS_D1)) * K2S_PITCH + 4 * lane);
+    const int s0 = k2s_slot(S, K2S_RS_D1), s1 = k2s_prev(s0, K2S_RS_D1);
+    const int i1 = k2s_slot(S, RS_IN), i0 = k2s_prev(i1, RS_IN), i2 = k2s_next(i1, RS_IN);
+    const K2SQuad q01 = k2s_ld4(d1 + (0 * K2S_RS_D1 + s0) * K2S_PITCH + 4 * lane);
+    const K2SQuad q10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + s0) * K2S_PITCH + 4 * lane);
+    const K2SQuad p10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + s1) * K2S_PITCH + 4 * lane);
     const float v01[5] = {k2s_up(q01.w), q01.x, q01.y, q01.z, q01.w};
     float m[4];
     const float is = k2s_sigma(A, R, lane, m);
@@ -577,8 +585,8 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *pl = in + c * RS_IN * K2S_PITCH + 4 * lane;
-        const K2SQuad b = k2s_ld4(pl + k2s_slot(S - 1, RS_IN) * K2S_PITCH), r = k2s_ld4(pl + k2s_slot(S, RS_IN) * K2S_PITCH);
-        const K2SQuad d = k2s_ld4(pl + k2s_slot(S + 1, RS_IN) * K2S_PITCH);
+        const K2SQuad b = k2s_ld4(pl + i0 * K2S_PITCH), r = k2s_ld4(pl + i1 * K2S_PITCH);
+        const K2SQuad d = k2s_ld4(pl + i2 * K2S_PITCH);
         const float r6[6] = {k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x)};
         float o[4], sv[4];
 #pragma unroll
@@ -609,11 +617,12 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
     if (!R.valid || k2s_row_kind(P, R.y, 0) != 0) return;
     const float *in = sm + K2S_OFF_P1;
     float r6[3][6], up[3][4], dn[3][4];
+    const int i1 = k2s_slot(S, K2S_RS_P1), i0 = k2s_prev(i1, K2S_RS_P1), i2 = k2s_next(i1, K2S_RS_P1);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *pl = in + c * K2S_RS_P1 * K2S_PITCH + 4 * lane;
-        const K2SQuad b = k2s_ld4(pl + k2s_slot(S - 1, K2S_RS_P1) * K2S_PITCH), r = k2s_ld4(pl + k2s_slot(S, K2S_RS_P1) * K2S_PITCH);
-        const K2SQuad d = k2s_ld4(pl + k2s_slot(S + 1, K2S_RS_P1) * K2S_PITCH);
+        const K2SQuad b = k2s_ld4(pl + i0 * K2S_PITCH), r = k2s_ld4(pl + i1 * K2S_PITCH);
+        const K2SQuad d = k2s_ld4(pl + i2 * K2S_PITCH);
         r6[c][0] = k2s_up(r.w); r6[c][1] = r.x; r6[c][2] = r.y; r6[c][3] = r.z; r6[c][4] = r.w; r6[c][5] = k2s_dn(r.x);
         up[c][0] = b.x; up[c][1] = b.y; up[c][2] = b.z; up[c][3] = b.w;
         dn[c][0] = d.x; dn[c][1] = d.y; dn[c][2] = d.z; dn[c][3] = d.w;

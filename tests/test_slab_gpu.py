@@ -14,7 +14,7 @@ HALO = _lib.HALO_ROWS
 
 @pytest.mark.parametrize("cfg", [dict(W=328, H=776, parts=3, iters=3, gab=True), dict(W=512, H=512, parts=2, iters=1, gab=True),
                                  dict(W=264, H=1032, parts=4, iters=2, gab=False)])
-@pytest.mark.parametrize("stage2", [_lib.STAGE2_AUTO, _lib.STAGE2_STAGED])
+@pytest.mark.parametrize("stage2", [_lib.STAGE2_AUTO, _lib.STAGE2_STREAM, _lib.STAGE2_TILE, _lib.STAGE2_STAGED])
 def test_slabs_match_whole_frame(recon, cfg, stage2):
     import torch
     W, H, parts = cfg["W"], cfg["H"], cfg["parts"]
@@ -70,7 +70,8 @@ def test_slabs_match_whole_frame(recon, cfg, stage2):
 
 @pytest.mark.parametrize("cfg", [dict(W=512, H=256, n=3, iters=1, gab=True), dict(W=264, H=320, n=4, iters=3, gab=True),
                                  dict(W=256, H=64, n=5, iters=2, gab=False), dict(W=384, H=512, n=1, iters=0, gab=True)])
-def test_batch_of_stacked_frames_matches_single_frames(recon, orc, cfg):
+@pytest.mark.parametrize("stage2", [_lib.STAGE2_AUTO, _lib.STAGE2_STREAM])
+def test_batch_of_stacked_frames_matches_single_frames(recon, orc, cfg, stage2):
     """jxlb200_vardct_reconstruct_batch_dev: n equally sized frames stacked vertically, stage 1 once over the stack, stage 2
     per frame.  Every frame must equal its own reconstruction (oracle for frame 0, the single-frame CUDA call for all): a
     varblock, chroma-from-luma tile or filter tap leaking across a frame boundary would show."""
@@ -85,11 +86,15 @@ def test_batch_of_stacked_frames_matches_single_frames(recon, orc, cfg):
     keys = ("qcoeff", "lf", "dct_select", "block_origin", "hf_mul", "sharpness", "x_from_y", "b_from_y")
     d = {k: torch.from_numpy(np.ascontiguousarray(np.concatenate([s[k] for s in sts], axis=-2))).to(dev) for k in keys}
     out = torch.full((3, H * n, W), np.nan, dtype=torch.float32, device=dev)
-    recon.reconstruct_batch_dev(p, n, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
-                                d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
-                                d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
-                                [out[c].data_ptr() for c in range(3)])
-    recon.sync()
+    recon.set_option(_lib.OPT_STAGE2, stage2)      # the stack goes through the stream kernel as one launch when forced (or large enough)
+    try:
+        recon.reconstruct_batch_dev(p, n, [d["qcoeff"][c].data_ptr() for c in range(3)], [d["lf"][c].data_ptr() for c in range(3)],
+                                    d["dct_select"].data_ptr(), d["block_origin"].data_ptr(), d["hf_mul"].data_ptr(),
+                                    d["x_from_y"].data_ptr(), d["b_from_y"].data_ptr(), d["sharpness"].data_ptr(),
+                                    [out[c].data_ptr() for c in range(3)])
+        recon.sync()
+    finally:
+        recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
     got = out.cpu().numpy()
     for f in range(n):
         assert np.array_equal(got[:, f * H:(f + 1) * H], singles[f]), "frame %d of the stack differs" % f

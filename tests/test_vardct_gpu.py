@@ -141,7 +141,7 @@ def _srgb_quantise(lin, bits):
     dict(shape=(264, 520), iters=0, gab=True),
     dict(shape=(256, 256), iters=0, gab=False),
 ])
-@pytest.mark.parametrize("stage2", ["staged", "auto", "pair", "stream", "fast"])
+@pytest.mark.parametrize("stage2", ["staged", "auto", "pair", "stream", "tile", "fast"])
 def test_full_reconstruction(recon, orc, cfg, stage2):
     W, H = cfg["shape"]
     p = default_frame_params(W, H, epf_iters=cfg["iters"], gab=cfg["gab"])
@@ -150,10 +150,11 @@ def test_full_reconstruction(recon, orc, cfg, stage2):
     if stage2 == "fast" and not (cfg["gab"] or cfg["iters"]):
         pytest.skip("nothing to fuse")
     try:
+        # auto = the faster of the two fused bit-exact kernels for the frame; stream = k2_stream wherever TMA applies; tile = k2_exact
         recon.set_option(_lib.OPT_STAGE2, {"staged": _lib.STAGE2_STAGED, "auto": _lib.STAGE2_AUTO, "pair": _lib.STAGE2_PAIR,
-                                           "stream": _lib.STAGE2_STREAM, "fast": _lib.STAGE2_FUSED}[stage2])
+                                           "stream": _lib.STAGE2_STREAM, "tile": _lib.STAGE2_TILE, "fast": _lib.STAGE2_FUSED}[stage2])
     except NotImplementedError:
-        pytest.skip("library built without this opt-in stage-2 variant (-DJXLB200_WITH_PAIR / -DJXLB200_WITH_STREAM)")
+        pytest.skip("library built without this opt-in stage-2 variant (-DJXLB200_WITH_PAIR)")
     try:
         got = recon.reconstruct(p, st)
     finally:

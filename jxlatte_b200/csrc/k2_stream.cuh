@@ -321,19 +321,29 @@ K2S_FN void k2s_final(const K2SArgs &A, const K2SRow &R, int lane, K2SQuad q[3])
 K2S_FN float k2s_wgt(float dist, float m, float ss, float is) {
     return fmaxf(K2S_SUB(1.0f, K2S_MUL(K2S_MUL(K2S_MUL(dist, m), ss), is)), 0.0f);
 }
-// the four divides of a row quad, a[j] / b[j] with r[j] = K2S_RCP(b[j]): one range test for the four numerators (kx_div_shared's
-// fast path is exact inside it, k2_exact.cuh) instead of one test, branch and reconvergence point per divide
-K2S_FN void k2s_div4(const float a[4], const float b[4], const float r[4], float o[4]) {
+// the twelve divides of a row quad (three channels), a[c][j] / b[j] with r[j] = K2S_RCP(b[j]): ONE range test for the twelve numerators
+// (kx_div_shared's fast path is exact inside it, k2_exact.cuh) instead of a test, a branch and a reconvergence point per divide, and
+// all the sums are complete before the first divide starts
+K2S_FN void k2s_div12(const float a[3][4], const float b[4], const float r[4], float o[3][4]) {
 #ifdef K2S_HOST_EMU
-    for (int j = 0; j < 4; j++) o[j] = a[j] / b[j];
+    for (int c = 0; c < 3; c++)
+        for (int j = 0; j < 4; j++) o[c][j] = a[c][j] / b[j];
 #else
-    const bool ok = kx_div_fast_ok(a[0]) & kx_div_fast_ok(a[1]) & kx_div_fast_ok(a[2]) & kx_div_fast_ok(a[3]);
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) ok = ok & kx_div_fast_ok(a[c][j]);
     if (ok) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) o[j] = kx_div_fast(a[j], b[j], r[j]);
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[c][j] = kx_div_fast(a[c][j], b[j], r[j]);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) o[j] = __fdiv_rn(a[j], b[j]);
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[c][j] = __fdiv_rn(a[c][j], b[j]);
     }
 #endif
 }
@@ -465,6 +475,86 @@ template <int DY, int DX> K2S_FN void k2s_d_pair(const K2Params &P, const float 
     }
 }
 
+// Pass 0: THREE maps of the same row pair in one task.  SET 0 = offsets (0,1), (1,1), (0,2) -> maps 0, 2, 4; SET 1 = (1,0), (1,-1), (2,0)
+// -> maps 1, 3, 5.  The maps of a set read the same input rows, so each row is loaded once per channel and its east (west) neighbours
+// are fetched once for all three; arithmetic and its order are those of k2s_d_pair, map by map.
+template <int SET> K2S_FN void k2s_d_triple(const K2Params &P, const float *in, float *maps, int S0, int lane) {
+    constexpr int DYS[3] = {SET == 0 ? 0 : 1, 1, SET == 0 ? 0 : 2};
+    constexpr int DXS[3] = {SET == 0 ? 1 : 0, SET == 0 ? 1 : -1, SET == 0 ? 2 : 0};
+    constexpr int NR = SET == 0 ? 5 : 6;                       // input rows S0-1 .. S0+2+max dy
+    float dist[3][2][4];
+    int off[NR];
+    off[0] = k2s_slot(S0 - 1, K2S_RS_GAB);
+#pragma unroll
+    for (int i = 1; i < NR; i++) off[i] = k2s_next(off[i - 1], K2S_RS_GAB);
+#pragma unroll
+    for (int i = 0; i < NR; i++) off[i] = off[i] * K2S_PITCH + 4 * lane;
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dist[m][k][j] = 0.0f;
+    const int nch = K2S_ROLLED_TRIPS(P);
+#pragma unroll 1
+    for (int c = 0; c < nch; c++) {
+        const float *pl = in + c * K2S_RS_GAB * K2S_PITCH;
+        float I[NR][4], e1[NR], e2[NR], w1[NR];                // the row's quad; columns x+4, x+5 and x-1 where a map of the set needs them
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const K2SQuad q = k2s_ld4(pl + off[i]);
+            I[i][0] = q.x; I[i][1] = q.y; I[i][2] = q.z; I[i][3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            e1[i] = 0.0f; e2[i] = 0.0f; w1[i] = 0.0f;
+            if (SET == 0) { e1[i] = k2s_dn(I[i][0]); if (i < 4) e2[i] = k2s_dn(I[i][1]); }     // (0,2) shifts rows 0..3 only
+            else if (i >= 1 && i < 5) w1[i] = k2s_up(I[i][3]);                                    // (1,-1) shifts rows 1..4
+        }
+        const float s = P.ch_scale[c];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const int DY = DYS[m], DX = DXS[m];
+            float T[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float *b = I[r], *v = I[r + DY];
+                float sh[4];
+                if (DX == 0) { sh[0] = v[0]; sh[1] = v[1]; sh[2] = v[2]; sh[3] = v[3]; }
+                else if (DX == 1) { sh[0] = v[1]; sh[1] = v[2]; sh[2] = v[3]; sh[3] = e1[r + DY]; }
+                else if (DX == 2) { sh[0] = v[2]; sh[1] = v[3]; sh[2] = e1[r + DY]; sh[3] = e2[r + DY]; }
+                else { sh[0] = w1[r + DY]; sh[1] = v[0]; sh[2] = v[1]; sh[3] = v[2]; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) T[r][j] = K2S_MUL(fabsf(K2S_SUB(b[j], sh[j])), s);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float *t = T[k + 1];
+                const float t6[6] = {k2s_up(t[3]), t[0], t[1], t[2], t[3], k2s_dn(t[0])};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float d = K2S_ADD(dist[m][k][j], t6[j + 1]);                   // (0, 0); the running sum starts at 0f like the Java's
+                    d = K2S_ADD(d, t6[j]);                                         // (0, -1)
+                    d = K2S_ADD(d, t6[j + 2]);                                     // (0, +1)
+                    d = K2S_ADD(d, T[k][j]);                                       // (-1, 0)
+                    d = K2S_ADD(d, T[k + 2][j]);                                   // (+1, 0)
+                    dist[m][k][j] = d;
+                }
+            }
+        }
+    }
+    const int so0 = k2s_slot(S0, K2S_RS_D0), so1 = k2s_next(so0, K2S_RS_D0);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        float *mp = maps + (2 * m + SET) * K2S_RS_D0 * K2S_PITCH + 4 * lane;
+        K2SQuad q0, q1;
+        q0.x = dist[m][0][0]; q0.y = dist[m][0][1]; q0.z = dist[m][0][2]; q0.w = dist[m][0][3];
+        q1.x = dist[m][1][0]; q1.y = dist[m][1][1]; q1.z = dist[m][1][2]; q1.w = dist[m][1][3];
+        k2s_st4(mp + so0 * K2S_PITCH, q0);
+        k2s_st4(mp + so1 * K2S_PITCH, q1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // W0: pass 0 (13-point double cross, Frame.java:44-55 crossList order) of stream row S: weights from the six maps, channel sums,
 // divide -> P0 ring.  Map order: 0 (0,1), 1 (1,0), 2 (1,1), 3 (1,-1), 4 (0,2), 5 (2,0); dist_{-d}(p) = map_d(p - d).
@@ -515,6 +605,7 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
         rsum[j] = K2S_RCP(s);
     }
     K2SQuad out[3];
+    float sv[3][4], ctr[3][4], o[3][4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *pl = in + c * K2S_RS_GAB * K2S_PITCH + 4 * lane;
@@ -524,7 +615,6 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
         const float b6[6] = {k2s_up(b.w), b.x, b.y, b.z, b.w, k2s_dn(b.x)};
         const float d6[6] = {k2s_up(d.w), d.x, d.y, d.z, d.w, k2s_dn(d.x)};
         const float r8[8] = {k2s_up(r.z), k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x), k2s_dn(r.y)};
-        float o[4], sv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = r8[j + 2];                                          // 0 + I * 1
@@ -540,11 +630,15 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
             s = K2S_ADD(s, K2S_MUL(r8[j + 4], w[j][9]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(e, j), w[j][10]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(a, j), w[j][11]));
-            sv[j] = s;
+            sv[c][j] = s;
+            ctr[c][j] = r8[j + 2];
         }
-        k2s_div4(sv, sumw, rsum, o);
-        if (pass) { o[0] = r8[2]; o[1] = r8[3]; o[2] = r8[4]; o[3] = r8[5]; }
-        out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
+    }
+    k2s_div12(sv, sumw, rsum, o);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        out[c].x = pass ? ctr[c][0] : o[c][0]; out[c].y = pass ? ctr[c][1] : o[c][1];
+        out[c].z = pass ? ctr[c][2] : o[c][2]; out[c].w = pass ? ctr[c][3] : o[c][3];
     }
     k2s_emit(P, ring, K2S_RS_P0, K2S_MARGIN_P0, R, S, lane, out);
     return 0;
@@ -582,13 +676,13 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
         rsum[j] = K2S_RCP(sumw[j]);
     }
     K2SQuad out[3];
+    float sv[3][4], ctr[3][4], o[3][4];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float *pl = in + c * RS_IN * K2S_PITCH + 4 * lane;
         const K2SQuad b = k2s_ld4(pl + i0 * K2S_PITCH), r = k2s_ld4(pl + i1 * K2S_PITCH);
         const K2SQuad d = k2s_ld4(pl + i2 * K2S_PITCH);
         const float r6[6] = {k2s_up(r.w), r.x, r.y, r.z, r.w, k2s_dn(r.x)};
-        float o[4], sv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = r6[j + 1];
@@ -596,11 +690,15 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
             s = K2S_ADD(s, K2S_MUL(r6[j + 2], w[j][1]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(b, j), w[j][2]));
             s = K2S_ADD(s, K2S_MUL(k2s_get(d, j), w[j][3]));
-            sv[j] = s;
+            sv[c][j] = s;
+            ctr[c][j] = r6[j + 1];
         }
-        k2s_div4(sv, sumw, rsum, o);
-        if (pass) { o[0] = r6[1]; o[1] = r6[2]; o[2] = r6[3]; o[3] = r6[4]; }
-        out[c].x = o[0]; out[c].y = o[1]; out[c].z = o[2]; out[c].w = o[3];
+    }
+    k2s_div12(sv, sumw, rsum, o);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        out[c].x = pass ? ctr[c][0] : o[c][0]; out[c].y = pass ? ctr[c][1] : o[c][1];
+        out[c].z = pass ? ctr[c][2] : o[c][2]; out[c].w = pass ? ctr[c][3] : o[c][3];
     }
     if (LAST) k2s_final(A, R, lane, out);
     else k2s_emit(P, ring, K2S_RS_P1, K2S_MARGIN_P1, R, S, lane, out);
@@ -664,10 +762,10 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
             sv[c][j] = s;
         }
     }
+    k2s_div12(sv, sumw, rsum, o);
+    if (pass) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        k2s_div4(sv[c], sumw, rsum, o[c]);
-        if (pass) { o[c][0] = r6[c][1]; o[c][1] = r6[c][2]; o[c][2] = r6[c][3]; o[c][3] = r6[c][4]; }
+        for (int c = 0; c < 3; c++) { o[c][0] = r6[c][1]; o[c][1] = r6[c][2]; o[c][2] = r6[c][3]; o[c][3] = r6[c][4]; }
     }
     K2SQuad out[3];
 #pragma unroll
@@ -765,18 +863,12 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
         }
         if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, t + 1, total, cur);     // lands while the other stages run
         if (ITERS == 3) {
-            // ---- D0: 6 maps x BAND / 2 row pairs, three tasks per warp; a warp's three tasks are three different maps ----
+            // ---- D0: 6 maps x BAND / 2 row pairs; a warp forms three maps of its row pair at once (they read the same input rows) ----
             {
                 const int S0 = S16 + Cfg::D0 + 2 * (warp & (K2S_BAND / 2 - 1));
-                float *m0 = d0, *m1 = d0 + K2S_RS_D0 * K2S_PITCH;
-                if (warp < K2S_BAND / 2) {
-                    k2s_d_task<0, 1>(A, gab, K2S_RS_GAB, m0, K2S_RS_D0, S0, total, lane);
-                    k2s_d_task<1, 1>(A, gab, K2S_RS_GAB, m0 + 2 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
-                    k2s_d_task<0, 2>(A, gab, K2S_RS_GAB, m0 + 4 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
-                } else {
-                    k2s_d_task<1, 0>(A, gab, K2S_RS_GAB, m1, K2S_RS_D0, S0, total, lane);
-                    k2s_d_task<1, -1>(A, gab, K2S_RS_GAB, m1 + 2 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
-                    k2s_d_task<2, 0>(A, gab, K2S_RS_GAB, m1 + 4 * K2S_RS_D0 * K2S_PITCH, K2S_RS_D0, S0, total, lane);
+                if (S0 + 1 >= 0 && S0 < total) {
+                    if (warp < K2S_BAND / 2) k2s_d_triple<0>(A.P, gab, d0, S0, lane);
+                    else k2s_d_triple<1>(A.P, gab, d0, S0, lane);
                 }
             }
             k2s_sync();

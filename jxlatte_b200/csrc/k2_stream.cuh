@@ -358,7 +358,7 @@ K2S_FN float k2s_sigma(const K2SArgs &A, const K2SRow &R, int lane, float m[4]) 
     m[2] = m[1];
     m[3] = (rowb || cb == 4) ? P.border_mul : 1.0f;
     col = col < 0 ? 0 : (col >= P.W ? P.W - 1 : col);         // lanes outside the frame produce values nobody keeps
-    return K2S_LDG(A.inv_sigma + (long long)R.z * A.zblk + (long long)(R.y >> 3) * P.wb + (col >> 3));
+    return K2S_LDG(A.inv_sigma + (R.z * A.zblk + (R.y >> 3) * P.wb + (col >> 3)));     // 32-bit index: k2_stream_supported checks the range
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -566,6 +566,8 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
     float *ring = sm + K2S_OFF_P0;
     const int kind = R.valid ? k2s_row_kind(P, R.y, K2S_MARGIN_P0) : 1;
     if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);                           // a global load: issued before anything else of the row
     const float *d0 = sm + K2S_OFF_D0;
     const int s0 = k2s_slot(S, K2S_RS_D0), s1 = k2s_prev(s0, K2S_RS_D0), s2 = k2s_prev(s1, K2S_RS_D0);
     const int g2 = k2s_slot(S, K2S_RS_GAB), g1 = k2s_prev(g2, K2S_RS_GAB), g0 = k2s_prev(g1, K2S_RS_GAB), g3 = k2s_next(g2, K2S_RS_GAB),
@@ -579,8 +581,6 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
     const float v02[6] = {e02a, e02b, q02.x, q02.y, q02.z, q02.w};       // map (0,2) at columns x-2 .. x+3
     const float u11[5] = {e11, p11.x, p11.y, p11.z, p11.w};              // map (1,1), row y-1, columns x-1 .. x+3
     const float u1m[5] = {p1m.x, p1m.y, p1m.z, p1m.w, e1m};              // map (1,-1), row y-1, columns x .. x+4
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));                            // copied through (Frame.java:608-612); also NaN
     const float ss = P.sigma_scale[0];
     float w[4][12], sumw[4], rsum[4];
@@ -654,6 +654,8 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
     float *ring = sm + K2S_OFF_P1;
     const int kind = R.valid ? k2s_row_kind(P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
     if (kind != 0) return kind;
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);
     const float *d1 = sm + K2S_OFF_D1;
     const int s0 = k2s_slot(S, K2S_RS_D1), s1 = k2s_prev(s0, K2S_RS_D1);
     const int i1 = k2s_slot(S, RS_IN), i0 = k2s_prev(i1, RS_IN), i2 = k2s_next(i1, RS_IN);
@@ -661,8 +663,6 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
     const K2SQuad q10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + s0) * K2S_PITCH + 4 * lane);
     const K2SQuad p10 = k2s_ld4(d1 + (1 * K2S_RS_D1 + s1) * K2S_PITCH + 4 * lane);
     const float v01[5] = {k2s_up(q01.w), q01.x, q01.y, q01.z, q01.w};
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));
     const float ss = P.sigma_scale[1];
     float w[4][4], sumw[4], rsum[4];
@@ -713,6 +713,8 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
     const K2Params &P = A.P;
     const K2SRow R = k2s_at(A, cur, S);
     if (!R.valid || k2s_row_kind(P, R.y, 0) != 0) return;
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);
     const float *in = sm + K2S_OFF_P1;
     float r6[3][6], up[3][4], dn[3][4];
     const int i1 = k2s_slot(S, K2S_RS_P1), i0 = k2s_prev(i1, K2S_RS_P1), i2 = k2s_next(i1, K2S_RS_P1);
@@ -741,8 +743,6 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
             vd[j] = c == 0 ? td : K2S_ADD(vd[j], td);
         }
     }
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);
     const bool pass = !(is <= (1.0f / 0.3f));
     const float ss = P.sigma_scale[2];
     float o[3][4], sv[3][4], sumw[4], rsum[4];
@@ -849,19 +849,32 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
 #ifdef K2S_HOST_EMU
     k2s_sync();
 #endif
+    // G of band `tb`: the band's rows have landed (mbarrier), one row per warp, then the barrier and the copies of rows below the frame
+    // (k2s_fixup), then the loads of the next band are issued -- they land while the other stages run
+#define K2S_G_PHASE(tb)                                                                                          \
+    {                                                                                                            \
+        K2S_WAIT_BAND(tb)                                                                                        \
+        const int Sg = K2S_BAND * (tb) + Cfg::G + warp;                                                          \
+        const int kindg = (Sg >= 0 && Sg < total) ? k2s_g_row<GAB>(A, sm, cur, Sg, lane) : 1;                    \
+        k2s_fixup(A, gab, K2S_RS_GAB, cur, kindg, Sg, lane);                                                     \
+        if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, (tb) + 1, total, cur);                              \
+    }
+#ifdef K2S_HOST_EMU
+#define K2S_WAIT_BAND(tb)
+#else
+#define K2S_WAIT_BAND(tb) if (K2S_BAND * (tb) < total) k2s_mbar_wait(bars + ((tb) & 1), ((tb) >> 1) & 1);
+#endif
+    // K2S_MERGE_G (epf_iters == 3): G runs one band ahead, in the same phase as D1 (they touch different rings; G's barrier is D1's too),
+    // so a tick has four barriers instead of five.  Measured SLOWER (8K frame: 1.406 ms against 1.370 ms), so it is off.
+#ifndef K2S_MERGE_G
+#define K2S_MERGE_G 0
+#endif
+    constexpr bool MERGE = ITERS == 3 && K2S_MERGE_G;
+    if (MERGE) K2S_G_PHASE(0)
 #pragma unroll 1
     for (int t = 0; t < n_ticks; t++) {
         const int S16 = K2S_BAND * t;
-        // ---- G ----
-#ifndef K2S_HOST_EMU
-        if (S16 < total) k2s_mbar_wait(bars + (t & 1), (t >> 1) & 1);
-#endif
-        {
-            const int S = S16 + Cfg::G + warp;
-            const int kind = (S >= 0 && S < total) ? k2s_g_row<GAB>(A, sm, cur, S, lane) : 1;
-            k2s_fixup(A, gab, K2S_RS_GAB, cur, kind, S, lane);
-        }
-        if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, t + 1, total, cur);     // lands while the other stages run
+        if (!MERGE) K2S_G_PHASE(t)
         if (ITERS == 3) {
             // ---- D0: 6 maps x BAND / 2 row pairs; a warp forms three maps of its row pair at once (they read the same input rows) ----
             {
@@ -885,7 +898,8 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             if (warp < K2S_BAND / 2) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
             else k2s_d_task<1, 0>(A, in1, RS1, d1 + K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, S0, total, lane);
         }
-        k2s_sync();
+        if (MERGE) K2S_G_PHASE(t + 1)      // GAB slots of band t + 1 were last read by W0 of this tick, two barriers ago
+        else k2s_sync();
         // ---- W1 ----
         {
             const int S = S16 + Cfg::W1 + warp;
@@ -897,10 +911,12 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             const int S = S16 + Cfg::P2 + warp;
             if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
         }
-        // epf_iters > 1: no barrier here -- G of tick t + 1 reads the RAW ring and writes GAB slots whose last readers ran before the
-        // barriers above.  epf_iters == 1: W1 has just read the GAB ring, and G is about to write it.
+        // epf_iters > 1: no barrier here -- the next phase (D0, or G when epf_iters == 2) writes rings whose last readers ran before
+        // the barriers above.  epf_iters == 1: W1 has just read the GAB ring, and G is about to write it.
         if (ITERS == 1) k2s_sync();
     }
+#undef K2S_G_PHASE
+#undef K2S_WAIT_BAND
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -972,6 +988,7 @@ static inline bool k2_stream_supported(const K2Params &K, int n_frames) {
     for (int c = 0; c < 3; c++)
         if (((uintptr_t)K.in[c] | (uintptr_t)K.out[c]) & 15) return false;
     if ((long long)K.rows * n_frames + 16 > 0x7fffffffll) return false;
+    if ((long long)((K.rows >> 3) + 2) * n_frames * K.wb > 0x7fffffffll) return false;       // k2s_sigma indexes the 1/sigma map with an int
     return true;
 }
 

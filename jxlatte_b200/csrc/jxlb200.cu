@@ -619,6 +619,15 @@ int32_t jxlb200_sync(jxlb200_ctx *ctx) {
 
 int64_t jxlb200_launch_count(jxlb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+#ifdef K2S_PHASE_TIMING
+// diagnostic builds only (tools/phase_timing.py): read and clear the per-stage cycle counters of k2_stream
+extern "C" int32_t jxlb200_debug_phase_clocks(unsigned long long out[16]) {
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyFromSymbol(out, k2s_phase_clk, sizeof(zero)) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(k2s_phase_clk, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int32_t jxlb200_set_option(jxlb200_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return JXLB200_E_ARG;
     if (option == JXLB200_OPT_STAGE2 && value >= 0 && value <= 6) {

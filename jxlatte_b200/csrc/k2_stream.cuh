@@ -826,6 +826,19 @@ template <int DY, int DX> K2S_FN void k2s_d_task(const K2SArgs &A, const float *
     if (S0 + 1 >= 0 && S0 < total) k2s_d_pair<DY, DX>(A.P, in, rs_in, outmap, rs_out, S0, lane);
 }
 
+// -DK2S_PHASE_TIMING (diagnostic builds only): cycles warp 1 spends working in each stage and waiting at the barrier that ends it,
+// summed over ticks and CTAs into k2s_phase_clk[2 * stage + {0 work, 1 wait}] (tools/phase_timing.py reads it)
+#if defined(K2S_PHASE_TIMING) && !defined(K2S_HOST_EMU)
+__device__ unsigned long long k2s_phase_clk[16];
+#define K2S_CLK_BEGIN long long clk_a = clock64(), clk_b;
+#define K2S_CLK_WORK(ph) clk_b = clock64(); if (tid == 32) atomicAdd(&k2s_phase_clk[2 * (ph)], (unsigned long long)(clk_b - clk_a)); clk_a = clk_b;
+#define K2S_CLK_WAIT(ph) clk_b = clock64(); if (tid == 32) atomicAdd(&k2s_phase_clk[2 * (ph) + 1], (unsigned long long)(clk_b - clk_a)); clk_a = clk_b;
+#else
+#define K2S_CLK_BEGIN
+#define K2S_CLK_WORK(ph)
+#define K2S_CLK_WAIT(ph)
+#endif
+
 template <int GAB, int ITERS>
 K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2) {
     using Cfg = K2SCfg<ITERS>;
@@ -854,9 +867,12 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
 #define K2S_G_PHASE(tb)                                                                                          \
     {                                                                                                            \
         K2S_WAIT_BAND(tb)                                                                                        \
+        K2S_CLK_WAIT(6)                                                                                          \
         const int Sg = K2S_BAND * (tb) + Cfg::G + warp;                                                          \
         const int kindg = (Sg >= 0 && Sg < total) ? k2s_g_row<GAB>(A, sm, cur, Sg, lane) : 1;                    \
+        K2S_CLK_WORK(0)                                                                                          \
         k2s_fixup(A, gab, K2S_RS_GAB, cur, kindg, Sg, lane);                                                     \
+        K2S_CLK_WAIT(0)                                                                                          \
         if (tid == 0) k2s_load_band(A, sm, bars, t0, t1, t2, (tb) + 1, total, cur);                              \
     }
 #ifdef K2S_HOST_EMU
@@ -870,6 +886,7 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
 #define K2S_MERGE_G 0
 #endif
     constexpr bool MERGE = ITERS == 3 && K2S_MERGE_G;
+    K2S_CLK_BEGIN
     if (MERGE) K2S_G_PHASE(0)
 #pragma unroll 1
     for (int t = 0; t < n_ticks; t++) {
@@ -884,12 +901,16 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
                     else k2s_d_triple<1>(A.P, gab, d0, S0, lane);
                 }
             }
+            K2S_CLK_WORK(1)
             k2s_sync();
+            K2S_CLK_WAIT(1)
             // ---- W0 ----
             {
                 const int S = S16 + Cfg::W0 + warp;
                 const int kind = (S >= 0 && S < total) ? k2s_w0_row(A, sm, cur, S, lane) : 1;
+                K2S_CLK_WORK(2)
                 k2s_fixup(A, p0, K2S_RS_P0, cur, kind, S, lane);
+                K2S_CLK_WAIT(2)
             }
         }
         // ---- D1: 2 maps x BAND / 2 row pairs ----
@@ -898,18 +919,23 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
             if (warp < K2S_BAND / 2) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
             else k2s_d_task<1, 0>(A, in1, RS1, d1 + K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, S0, total, lane);
         }
+        K2S_CLK_WORK(3)
         if (MERGE) K2S_G_PHASE(t + 1)      // GAB slots of band t + 1 were last read by W0 of this tick, two barriers ago
         else k2s_sync();
+        K2S_CLK_WAIT(3)
         // ---- W1 ----
         {
             const int S = S16 + Cfg::W1 + warp;
             const int kind = (S >= 0 && S < total) ? k2s_w1_row<RS1, ITERS == 1>(A, sm, in1, cur, S, lane) : 1;
+            K2S_CLK_WORK(4)
             if (ITERS > 1) k2s_fixup(A, p1, K2S_RS_P1, cur, kind, S, lane);
+            K2S_CLK_WAIT(4)
         }
         // ---- P2 ----
         if (ITERS > 1) {
             const int S = S16 + Cfg::P2 + warp;
             if (S >= 0 && S < total) k2s_p2_row(A, sm, cur, S, lane);
+            K2S_CLK_WORK(5)
         }
         // epf_iters > 1: no barrier here -- the next phase (D0, or G when epf_iters == 2) writes rings whose last readers ran before
         // the barriers above.  epf_iters == 1: W1 has just read the GAB ring, and G is about to write it.

@@ -269,10 +269,12 @@ int invert_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const int32_t *c
     cudaStream_t *ks = ctx->k1_stream;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
     for (int i = 0; i < 6; i++) CUDA_TRY(ctx, cudaStreamWaitEvent(ks[i], ctx->ev_fork, 0));
+    // the big column passes go first: every row pass waits for all of them, small / medium fill the SMs they leave (measured: 2.50 ->
+    // 2.47 ms per 8K step; stream priorities change nothing)
+    launch_big<256, 0>(ctx, P, 3, ks[5]); launch_big<128, 0>(ctx, P, 2, ks[4]); launch_big<64, 0>(ctx, P, 1, ks[3]); launch_big<32, 0>(ctx, P, 0, ks[2]);
     k1_small<<<min(ctx->sms * 8, ceil_div(ncells, SMALL_BATCH)), 128, 0, ks[0]>>>(P, S, ctx->items.as<int>());
     k1_medium<<<min(ctx->sms * 4, ceil_div(ncells, 2)), 256, 0, ks[1]>>>(P, S, ctx->items.as<int>());
     ctx->launches += 2;
-    launch_big<256, 0>(ctx, P, 3, ks[5]); launch_big<128, 0>(ctx, P, 2, ks[4]); launch_big<64, 0>(ctx, P, 1, ks[3]); launch_big<32, 0>(ctx, P, 0, ks[2]);
     for (int k = 0; k < 4; k++) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_p0[k], ks[2 + k]));
     for (int k = 0; k < 4; k++)
         for (int j = 0; j < 4; j++)

@@ -1010,7 +1010,7 @@ static inline cudaError_t k2_stream_init_all() {
 }
 // the TMA path needs 16-byte aligned planes and pitches that are multiples of 4 floats; anything else stays on k2_exact
 static inline bool k2_stream_supported(const K2Params &K, int n_frames) {
-    if (K.iters < 1 || K.rows < 8 || K.W < 8 || (K.in_pitch & 3) || (K.out_pitch & 3) || !k2s_encoder()) return false;
+    if (K.iters < 1 || K.rows < 8 || K.W < 8 || (K.rows & 7) || (K.W & 7) || (K.in_pitch & 3) || (K.out_pitch & 3) || !k2s_encoder()) return false;
     for (int c = 0; c < 3; c++)
         if (((uintptr_t)K.in[c] | (uintptr_t)K.out[c]) & 15) return false;
     if ((long long)K.rows * n_frames + 16 > 0x7fffffffll) return false;

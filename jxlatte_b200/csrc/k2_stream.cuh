@@ -329,12 +329,17 @@ K2S_FN void k2s_div12(const float a[3][4], const float b[4], const float r[4], f
     for (int c = 0; c < 3; c++)
         for (int j = 0; j < 4; j++) o[c][j] = a[c][j] / b[j];
 #else
-    bool ok = true;
+    // smallest and largest magnitude of the twelve (a NaN numerator drops out of both and takes the fast path, where it stays a NaN)
+    float lo = fabsf(a[0][0]), hi = lo;
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) ok = ok & kx_div_fast_ok(a[c][j]);
-    if (ok) {
+        for (int j = 0; j < 4; j++) {
+            if (c + j == 0) continue;
+            lo = fminf(lo, fabsf(a[c][j]));
+            hi = fmaxf(hi, fabsf(a[c][j]));
+        }
+    if (lo >= 7.8886090522101181e-31f && hi <= 1.2676506002282294e30f) {        // kx_div_fast_ok for all of them
 #pragma unroll
         for (int c = 0; c < 3; c++)
 #pragma unroll

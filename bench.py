@@ -351,7 +351,7 @@ def run_ours(args):
             rec.sync()
         peak, which = peaks()
         # stage 2 of a frame this size with Gaborish on is the stream kernel (csrc/jxlb200.cu: stream_pays), else the tile kernel
-        k2_name = ("k2_stream (persistent, TMA-fed row rings: fused Gaborish+EPF+colour, bit-exact)" if (W * H >= 600000 and p.gab and iters >= 1)
+        k2_name = ("k2_stream (persistent, TMA-fed row rings: fused Gaborish+EPF+colour, bit-exact)" if (W * H >= 600000 and (p.gab or iters == 3) and iters >= 1)
                    else "k2_exact (fused Gaborish+EPF+colour, bit-exact)")
         if os.environ.get("JXLB200_STAGE2"):
             k2_name = "stage 2 as selected by JXLB200_STAGE2=%s" % os.environ["JXLB200_STAGE2"]

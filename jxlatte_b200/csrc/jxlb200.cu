@@ -413,11 +413,12 @@ int restore_dev(jxlb200_ctx *ctx, const jxlb200_frame_params *p, const jxlb200_s
                                                                                          ctx->lut8.as<float>(), inv_sigma, ctx->flags.as<int>());
         ctx->launches++;
     }
-    // Two bit-exact fused kernels.  Default: the stream kernel where it is the faster one (Gaborish on, at least 0.6 MP: 8K frame, gab +
-    // EPF 3: 1.52 ms against 1.66 ms; without Gaborish its copy stage costs more than the tile kernel's halo, and a small frame does not
-    // fill 148 persistent CTAs -- tools/stage2_matrix.py, profiles/r2_stage2_matrix.md), else the tile kernel.  5 forces the stream
-    // kernel wherever the planes can take TMA (16-byte aligned bases and pitches, epf_iters >= 1), 6 forces the tile kernel.
-    const bool stream_pays = K.gab && (long long)K.W * K.rows * n_frames >= 600000ll;
+    // Two bit-exact fused kernels.  Default: the stream kernel where it is the faster one -- at least 0.6 MP, and Gaborish on or three EPF
+    // passes (8K frame, gab + EPF 3: 1.36 ms against 1.66 ms; without Gaborish its first stage is a plain copy, which only three passes of
+    // filtering outweigh, and a small frame does not fill 148 persistent CTAs: tools/stage2_matrix.py, profiles/r2_stage2_matrix.md) --
+    // else the tile kernel.  5 forces the stream kernel wherever the planes can take TMA (16-byte aligned bases and pitches, sizes that are
+    // multiples of 8, epf_iters >= 1), 6 forces the tile kernel.
+    const bool stream_pays = (K.gab || K.iters == 3) && (long long)K.W * K.rows * n_frames >= 600000ll;
     if (((ctx->opt_stage2 == 0 && stream_pays) || ctx->opt_stage2 == 5) && k2_stream_supported(K, n_frames) &&
         k2_stream_launch(K, inv_sigma, st, n_frames, ctx->sms) == 0) {
         ctx->launches++;

@@ -1,5 +1,6 @@
-"""Stage-2 time of the two bit-exact kernels (JXLB200_OPT_STAGE2 0 = k2_stream where TMA applies, 6 = the tile kernel k2_exact) for
-every (gab, epf_iters) and a few frame shapes; prints one line per case with both times and whether the planes agree bit for bit."""
+"""Stage-2 time of the two bit-exact fused kernels for every (gab, epf_iters) and a few frame shapes: JXLB200_OPT_STAGE2 = 0 (the
+library's choice), 5 (k2_stream forced), 6 (the tile kernel k2_exact forced); one line per case with the three times and whether the
+planes agree bit for bit.  The dispatch rule in csrc/jxlb200.cu (stream_pays) is read off this table."""
 import os, sys, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -30,11 +31,12 @@ for (W, H) in ((7680, 4320), (2048, 2048), (1280, 720), (512, 512)):
         for it in (3, 2, 1):
             p = default_frame_params(W, H, epf_iters=it, gab=bool(gab))
             res = {}
-            for opt in (_lib.STAGE2_AUTO, _lib.STAGE2_TILE):
+            for opt in (_lib.STAGE2_AUTO, _lib.STAGE2_STREAM, _lib.STAGE2_TILE):
                 rec.set_option(_lib.OPT_STAGE2, opt)
                 t = timed(lambda: rec.restore_dev(p, None, x, W, hm.data_ptr(), sh.data_ptr(), o))
                 rec.sync()
                 res[opt] = (t, zlib.crc32(out.cpu().numpy().tobytes()))
             rec.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
-            a, b = res[_lib.STAGE2_AUTO], res[_lib.STAGE2_TILE]
-            print("%5dx%-5d gab %d epf %d: stream %.3f ms  tile %.3f ms  ratio %.2f  same bits %s" % (W, H, gab, it, a[0], b[0], a[0] / b[0], a[1] == b[1]), flush=True)
+            a, f, b = res[_lib.STAGE2_AUTO], res[_lib.STAGE2_STREAM], res[_lib.STAGE2_TILE]
+            print("%5dx%-5d gab %d epf %d: default %.3f ms  stream %.3f ms  tile %.3f ms  default/tile %.2f  stream/tile %.2f  same bits %s"
+                  % (W, H, gab, it, a[0], f[0], b[0], a[0] / b[0], f[0] / b[0], a[1] == b[1] and f[1] == b[1]), flush=True)

@@ -45,28 +45,21 @@
 #define K2S_ADD(a, b) ((a) + (b))   /* host build uses -ffp-contract=off */
 #define K2S_SUB(a, b) ((a) - (b))
 #define K2S_MUL(a, b) ((a) * (b))
-#define K2S_RCP(b) (0.0f)
-#define K2S_DIVS(a, b, r) ((a) / (b))
-
+#define K2S_RCP(b) (0.0f)             /* the host divides; the device shares one refined reciprocal per pixel (k2s_div12) */
 #define K2S_LDG(p) (*(p))
 #else
 #include <cuda.h>
-#include "k2_exact.cuh"             /* kx_rcp_refined / kx_div_shared: the three divides of a pixel share one refined reciprocal */
+#include "k2_exact.cuh"             /* kx_rcp_refined / kx_div_fast: the three divides of a pixel share one refined reciprocal */
 #define K2S_FN __device__ __forceinline__
 #define K2S_ADD(a, b) __fadd_rn((a), (b))
 #define K2S_SUB(a, b) __fsub_rn((a), (b))
 #define K2S_MUL(a, b) __fmul_rn((a), (b))
 #define K2S_RCP(b) kx_rcp_refined(b)
-#define K2S_DIVS(a, b, r) kx_div_shared((a), (b), (r))
-
 #define K2S_LDG(p) __ldg(p)
 #endif
 
-#ifdef K2S_UNROLL_CHANNELS
-#define K2S_ROLLED_TRIPS(P) 3
-#else
+// trip count of the channel loops that must stay rolled: read from a kernel argument, or the compiler unrolls them whatever the pragma says
 #define K2S_ROLLED_TRIPS(P) ((P).W > 0 ? 3 : 0)
-#endif
 #define K2S_TW 112            /* useful columns of a column strip */
 #define K2S_HALO 8            /* halo columns each side and halo rows each side of an item (7 used: 1 + 3 + 2 + 1) */
 #define K2S_PITCH 128         /* floats per ring row: 32 lanes x 4 */

@@ -45,6 +45,8 @@
 #define K2S_ADD(a, b) ((a) + (b))   /* host build uses -ffp-contract=off */
 #define K2S_SUB(a, b) ((a) - (b))
 #define K2S_MUL(a, b) ((a) * (b))
+static inline float k2s_host_subsat(float a, float b) { const float t = a - b; return t > 0.0f ? (t > 1.0f ? 1.0f : t) : 0.0f; }
+#define K2S_SUBSAT(a, b) k2s_host_subsat((a), (b))
 #define K2S_RCP(b) (0.0f)             /* the host divides; the device shares one refined reciprocal per pixel (k2s_div12) */
 #define K2S_LDG(p) (*(p))
 #else
@@ -54,6 +56,8 @@
 #define K2S_ADD(a, b) __fadd_rn((a), (b))
 #define K2S_SUB(a, b) __fsub_rn((a), (b))
 #define K2S_MUL(a, b) __fmul_rn((a), (b))
+__device__ __forceinline__ float k2s_subsat(float a, float b) { float r; asm("sub.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#define K2S_SUBSAT(a, b) k2s_subsat((a), (b))
 #define K2S_RCP(b) kx_rcp_refined(b)
 #define K2S_LDG(p) __ldg(p)
 #endif
@@ -131,6 +135,7 @@ int k2s_emu_tid();
 int k2s_emu_cta();
 int k2s_emu_grid();
 float k2s_emu_shfl(float v, int src_lane);
+int k2s_emu_any(int pred);
 void k2s_emu_sync();
 int k2s_emu_sync_or(int pred);
 struct K2STmap { const float *base; int w, rows; long long pitch; };
@@ -140,6 +145,7 @@ K2S_FN int k2s_grid() { return k2s_emu_grid(); }
 K2S_FN float k2s_up(float v) { const int l = k2s_emu_tid() & 31; return k2s_emu_shfl(v, l > 0 ? l - 1 : l); }
 K2S_FN float k2s_dn(float v) { const int l = k2s_emu_tid() & 31; return k2s_emu_shfl(v, l < 31 ? l + 1 : l); }
 K2S_FN float k2s_from(float v, int src) { return k2s_emu_shfl(v, src); }
+K2S_FN bool k2s_any(bool pred) { return k2s_emu_any(pred) != 0; }
 K2S_FN void k2s_sync() { k2s_emu_sync(); }
 K2S_FN int k2s_sync_or(int pred) { return k2s_emu_sync_or(pred); }
 struct K2SQuad { float x, y, z, w; };
@@ -164,6 +170,7 @@ K2S_FN int k2s_grid() { return gridDim.x; }
 K2S_FN float k2s_up(float v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 K2S_FN float k2s_dn(float v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 K2S_FN float k2s_from(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+K2S_FN bool k2s_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
 K2S_FN void k2s_sync() { __syncthreads(); }
 K2S_FN int k2s_sync_or(int pred) { return __syncthreads_or(pred); }
 K2S_FN K2SQuad k2s_ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -311,8 +318,15 @@ K2S_FN void k2s_final(const K2SArgs &A, const K2SRow &R, int lane, K2SQuad q[3])
 }
 
 // epfWeight (Frame.java:671-679): m = borderSadMul on block-border pixels, else 1 (x * 1 is exact)
-K2S_FN float k2s_wgt(float dist, float m, float ss, float is) {
-    return fmaxf(K2S_SUB(1.0f, K2S_MUL(K2S_MUL(K2S_MUL(dist, m), ss), is)), 0.0f);
+// epfWeight's clamp v < 0 ? 0 : v with v = 1 - x.  SAT: ONE saturating subtract (FADD.SAT) -- when x >= 0, v <= 1 and clamping at 1
+// changes nothing (a NaN becomes 0 either way).  x is a sum of magnitudes times scales k2_stream_supported checks to be non-negative,
+// times 1/sigma: the row functions take the SAT form unless a lane of the warp has 1/sigma < 0 (an HF multiplier <= 0, which a crafted
+// stream can carry: HFMetadata.java:49), and the literal form for such a row.
+template <bool SAT> K2S_FN float k2s_wgt(float dist, float m, float ss, float is) {
+    const float x = K2S_MUL(K2S_MUL(K2S_MUL(dist, m), ss), is);
+    if (SAT) return K2S_SUBSAT(1.0f, x);
+    const float v = K2S_SUB(1.0f, x);
+    return v < 0.0f ? 0.0f : v;                               // Frame.java:677-678, literally
 }
 // the twelve divides of a row quad (three channels), a[c][j] / b[j] with r[j] = K2S_RCP(b[j]): ONE range test for the twelve numerators
 // (kx_div_shared's fast path is exact inside it, k2_exact.cuh) instead of a test, a branch and a reconvergence point per divide, and
@@ -557,15 +571,10 @@ template <int SET> K2S_FN void k2s_d_triple(const K2Params &P, const float *in, 
 // W0: pass 0 (13-point double cross, Frame.java:44-55 crossList order) of stream row S: weights from the six maps, channel sums,
 // divide -> P0 ring.  Map order: 0 (0,1), 1 (1,0), 2 (1,1), 3 (1,-1), 4 (0,2), 5 (2,0); dist_{-d}(p) = map_d(p - d).
 // ------------------------------------------------------------------------------------------------------------------------
-K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
+template <bool SAT> K2S_FN void k2s_w0_body(const K2SArgs &A, float *sm, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
     const K2Params &P = A.P;
-    const K2SRow R = k2s_at(A, cur, S);
     const float *in = sm + K2S_OFF_GAB;
     float *ring = sm + K2S_OFF_P0;
-    const int kind = R.valid ? k2s_row_kind(P, R.y, K2S_MARGIN_P0) : 1;
-    if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);                           // a global load: issued before anything else of the row
     const float *d0 = sm + K2S_OFF_D0;
     const int s0 = k2s_slot(S, K2S_RS_D0), s1 = k2s_prev(s0, K2S_RS_D0), s2 = k2s_prev(s1, K2S_RS_D0);
     const int g2 = k2s_slot(S, K2S_RS_GAB), g1 = k2s_prev(g2, K2S_RS_GAB), g0 = k2s_prev(g1, K2S_RS_GAB), g3 = k2s_next(g2, K2S_RS_GAB),
@@ -584,18 +593,18 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
     float w[4][12], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        w[j][0] = k2s_wgt(v01[j], m[j], ss, is);                         // (0,-1) = -(0,1): map at (y, x-1)
-        w[j][1] = k2s_wgt(v01[j + 1], m[j], ss, is);                     // (0, 1)
-        w[j][2] = k2s_wgt(k2s_get(p10, j), m[j], ss, is);                // (-1,0) = -(1,0): map at (y-1, x)
-        w[j][3] = k2s_wgt(k2s_get(q10, j), m[j], ss, is);                // (1, 0)
-        w[j][4] = k2s_wgt(u1m[j + 1], m[j], ss, is);                     // (-1,1) = -(1,-1): map at (y-1, x+1)
-        w[j][5] = k2s_wgt(k2s_get(q11, j), m[j], ss, is);                // (1, 1)
-        w[j][6] = k2s_wgt(k2s_get(q1m, j), m[j], ss, is);                // (1,-1)
-        w[j][7] = k2s_wgt(u11[j], m[j], ss, is);                         // (-1,-1) = -(1,1): map at (y-1, x-1)
-        w[j][8] = k2s_wgt(v02[j], m[j], ss, is);                         // (0,-2) = -(0,2): map at (y, x-2)
-        w[j][9] = k2s_wgt(v02[j + 2], m[j], ss, is);                     // (0, 2)
-        w[j][10] = k2s_wgt(k2s_get(q20, j), m[j], ss, is);               // (2, 0)
-        w[j][11] = k2s_wgt(k2s_get(p20, j), m[j], ss, is);               // (-2,0) = -(2,0): map at (y-2, x)
+        w[j][0] = k2s_wgt<SAT>(v01[j], m[j], ss, is);                         // (0,-1) = -(0,1): map at (y, x-1)
+        w[j][1] = k2s_wgt<SAT>(v01[j + 1], m[j], ss, is);                     // (0, 1)
+        w[j][2] = k2s_wgt<SAT>(k2s_get(p10, j), m[j], ss, is);                // (-1,0) = -(1,0): map at (y-1, x)
+        w[j][3] = k2s_wgt<SAT>(k2s_get(q10, j), m[j], ss, is);                // (1, 0)
+        w[j][4] = k2s_wgt<SAT>(u1m[j + 1], m[j], ss, is);                     // (-1,1) = -(1,-1): map at (y-1, x+1)
+        w[j][5] = k2s_wgt<SAT>(k2s_get(q11, j), m[j], ss, is);                // (1, 1)
+        w[j][6] = k2s_wgt<SAT>(k2s_get(q1m, j), m[j], ss, is);                // (1,-1)
+        w[j][7] = k2s_wgt<SAT>(u11[j], m[j], ss, is);                         // (-1,-1) = -(1,1): map at (y-1, x-1)
+        w[j][8] = k2s_wgt<SAT>(v02[j], m[j], ss, is);                         // (0,-2) = -(0,2): map at (y, x-2)
+        w[j][9] = k2s_wgt<SAT>(v02[j + 2], m[j], ss, is);                     // (0, 2)
+        w[j][10] = k2s_wgt<SAT>(k2s_get(q20, j), m[j], ss, is);               // (2, 0)
+        w[j][11] = k2s_wgt<SAT>(k2s_get(p20, j), m[j], ss, is);               // (-2,0) = -(2,0): map at (y-2, x)
         float s = 1.0f;                                                  // 0 + weight(centre) = 1
 #pragma unroll
         for (int k = 0; k < 12; k++) s = K2S_ADD(s, w[j][k]);
@@ -639,6 +648,15 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
         out[c].z = pass ? ctr[c][2] : o[c][2]; out[c].w = pass ? ctr[c][3] : o[c][3];
     }
     k2s_emit(P, ring, K2S_RS_P0, K2S_MARGIN_P0, R, S, lane, out);
+}
+K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
+    const K2SRow R = k2s_at(A, cur, S);
+    const int kind = R.valid ? k2s_row_kind(A.P, R.y, K2S_MARGIN_P0) : 1;
+    if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);                           // a global load: issued before anything else of the row
+    if (k2s_any(is < 0.0f)) k2s_w0_body<false>(A, sm, R, S, lane, is, m);
+    else k2s_w0_body<true>(A, sm, R, S, lane, is, m);
     return 0;
 }
 
@@ -646,14 +664,10 @@ K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int la
 // W1: pass 1 (5-point cross) of stream row S from the two maps; input ring = P0 (epf_iters == 3) or GAB.  LAST: epf_iters == 1,
 // the row goes through the colour transform to HBM instead of the P1 ring.
 // ------------------------------------------------------------------------------------------------------------------------
-template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *sm, const float *in, K2SCursor &cur, int S, int lane) {
+template <int RS_IN, bool LAST, bool SAT>
+K2S_FN void k2s_w1_body(const K2SArgs &A, float *sm, const float *in, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
     const K2Params &P = A.P;
-    const K2SRow R = k2s_at(A, cur, S);
     float *ring = sm + K2S_OFF_P1;
-    const int kind = R.valid ? k2s_row_kind(P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
-    if (kind != 0) return kind;
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);
     const float *d1 = sm + K2S_OFF_D1;
     const int s0 = k2s_slot(S, K2S_RS_D1), s1 = k2s_prev(s0, K2S_RS_D1);
     const int i1 = k2s_slot(S, RS_IN), i0 = k2s_prev(i1, RS_IN), i2 = k2s_next(i1, RS_IN);
@@ -666,10 +680,10 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
     float w[4][4], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        w[j][0] = k2s_wgt(v01[j], m[j], ss, is);
-        w[j][1] = k2s_wgt(v01[j + 1], m[j], ss, is);
-        w[j][2] = k2s_wgt(k2s_get(p10, j), m[j], ss, is);
-        w[j][3] = k2s_wgt(k2s_get(q10, j), m[j], ss, is);
+        w[j][0] = k2s_wgt<SAT>(v01[j], m[j], ss, is);
+        w[j][1] = k2s_wgt<SAT>(v01[j + 1], m[j], ss, is);
+        w[j][2] = k2s_wgt<SAT>(k2s_get(p10, j), m[j], ss, is);
+        w[j][3] = k2s_wgt<SAT>(k2s_get(q10, j), m[j], ss, is);
         sumw[j] = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w[j][0]), w[j][1]), w[j][2]), w[j][3]);
         rsum[j] = K2S_RCP(sumw[j]);
     }
@@ -700,6 +714,15 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
     }
     if (LAST) k2s_final(A, R, lane, out);
     else k2s_emit(P, ring, K2S_RS_P1, K2S_MARGIN_P1, R, S, lane, out);
+}
+template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *sm, const float *in, K2SCursor &cur, int S, int lane) {
+    const K2SRow R = k2s_at(A, cur, S);
+    const int kind = R.valid ? k2s_row_kind(A.P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
+    if (kind != 0) return kind;
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);
+    if (k2s_any(is < 0.0f)) k2s_w1_body<RS_IN, LAST, false>(A, sm, in, R, S, lane, is, m);
+    else k2s_w1_body<RS_IN, LAST, true>(A, sm, in, R, S, lane, is, m);
     return 0;
 }
 
@@ -707,12 +730,8 @@ template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *s
 // P2: pass 2 (5-point cross, point differences: epfDistance2, Frame.java:657-669) of stream row S from the P1 ring, then the
 // colour transform and the store.  Everything stays in registers.
 // ------------------------------------------------------------------------------------------------------------------------
-K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
+template <bool SAT> K2S_FN void k2s_p2_body(const K2SArgs &A, float *sm, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
     const K2Params &P = A.P;
-    const K2SRow R = k2s_at(A, cur, S);
-    if (!R.valid || k2s_row_kind(P, R.y, 0) != 0) return;
-    float m[4];
-    const float is = k2s_sigma(A, R, lane, m);
     const float *in = sm + K2S_OFF_P1;
     float r6[3][6], up[3][4], dn[3][4];
     const int i1 = k2s_slot(S, K2S_RS_P1), i0 = k2s_prev(i1, K2S_RS_P1), i2 = k2s_next(i1, K2S_RS_P1);
@@ -746,8 +765,8 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
     float o[3][4], sv[3][4], sumw[4], rsum[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const float w0 = k2s_wgt(h[j], m[j], ss, is), w1 = k2s_wgt(h[j + 1], m[j], ss, is);
-        const float w2 = k2s_wgt(vu[j], m[j], ss, is), w3 = k2s_wgt(vd[j], m[j], ss, is);
+        const float w0 = k2s_wgt<SAT>(h[j], m[j], ss, is), w1 = k2s_wgt<SAT>(h[j + 1], m[j], ss, is);
+        const float w2 = k2s_wgt<SAT>(vu[j], m[j], ss, is), w3 = k2s_wgt<SAT>(vd[j], m[j], ss, is);
         sumw[j] = K2S_ADD(K2S_ADD(K2S_ADD(K2S_ADD(1.0f, w0), w1), w2), w3);
         rsum[j] = K2S_RCP(sumw[j]);
 #pragma unroll
@@ -769,6 +788,14 @@ K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int l
 #pragma unroll
     for (int c = 0; c < 3; c++) { out[c].x = o[c][0]; out[c].y = o[c][1]; out[c].z = o[c][2]; out[c].w = o[c][3]; }
     k2s_final(A, R, lane, out);
+}
+K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
+    const K2SRow R = k2s_at(A, cur, S);
+    if (!R.valid || k2s_row_kind(A.P, R.y, 0) != 0) return;
+    float m[4];
+    const float is = k2s_sigma(A, R, lane, m);
+    if (k2s_any(is < 0.0f)) k2s_p2_body<false>(A, sm, R, S, lane, is, m);
+    else k2s_p2_body<true>(A, sm, R, S, lane, is, m);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -1013,6 +1040,14 @@ static inline bool k2_stream_supported(const K2Params &K, int n_frames) {
         if (((uintptr_t)K.in[c] | (uintptr_t)K.out[c]) & 15) return false;
     if ((long long)K.rows * n_frames + 16 > 0x7fffffffll) return false;
     if ((long long)((K.rows >> 3) + 2) * n_frames * K.wb > 0x7fffffffll) return false;       // k2s_sigma indexes the 1/sigma map with an int
+    // k2s_wgt clamps 1 - x with one saturating subtract, which equals the reference's max(1 - x, 0) when x >= 0: every frame-level factor
+    // of x must be non-negative (they are in every real stream; a frame with a negative scale goes to the tile kernel); the per-block
+    // factor 1/sigma is checked row by row in the kernel
+    if (!(K.border_mul >= 0.0f) || !(K.gscale > 0.0f)) return false;
+    for (int i = 0; i < 3; i++)
+        if (!(K.ch_scale[i] >= 0.0f) || !(K.sigma_scale[i] >= 0.0f)) return false;
+    for (int i = 0; i < 8; i++)
+        if (!(K.sharp_lut[i] >= 0.0f)) return false;
     return true;
 }
 

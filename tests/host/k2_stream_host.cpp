@@ -34,6 +34,15 @@ float k2s_emu_shfl(float v, int src_lane) {
     pthread_barrier_wait(&g.warp_bar[w]);
     return r;
 }
+int k2s_emu_any(int pred) {
+    const int w = t_tid >> 5, l = t_tid & 31;
+    g.xch[w * 32 + l] = pred ? 1.0f : 0.0f;
+    pthread_barrier_wait(&g.warp_bar[w]);
+    int r = 0;
+    for (int i = 0; i < 32; i++) r |= g.xch[w * 32 + i] != 0.0f;
+    pthread_barrier_wait(&g.warp_bar[w]);
+    return r;
+}
 void k2s_emu_sync() { pthread_barrier_wait(&g.cta_bar); }
 int k2s_emu_sync_or(int pred) {
     if (pred) __atomic_store_n(&g.any[g.any_phase[t_tid] & 1], 1, __ATOMIC_RELAXED);

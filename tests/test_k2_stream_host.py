@@ -86,6 +86,25 @@ def test_whole_frame_bit_exact(emu, orc, cfg):
     assert np.array_equal(got, want), "max abs err %g at %s" % (np.nanmax(np.abs(got - want)), np.argwhere(~(got == want))[:4])
 
 
+@pytest.mark.parametrize("iters", [1, 2, 3])
+def test_non_positive_hf_multipliers_bit_exact(emu, orc, iters):
+    """HFMetadata takes the HF multiplier as 1 + a Modular-decoded value (HFMetadata.java:49), so a crafted stream can make it zero or
+    negative: sigma and 1/sigma are then infinite or negative and epfWeight's 1 - x exceeds 1.  The row functions clamp with a
+    saturating subtract only where every 1/sigma of the warp's row is non-negative; rows with such blocks take the literal form."""
+    W, H = 136, 72
+    p = default_frame_params(W, H, epf_iters=iters)
+    rng = np.random.default_rng(4242 + iters)
+    planes = _planes(rng, H, W)
+    hm, sh = _maps(rng, H, W)
+    hm[rng.random(hm.shape) < 0.2] = -3
+    hm[rng.random(hm.shape) < 0.1] = 0
+    sh[(hm < 0) & (sh == 0)] = 5        # sharpness 0 (sigma = -0, 1/sigma = -inf) would breed NaNs, which the reference's clamp passes on and a hardware max does not
+    want = _oracle(orc, p, planes, hm, sh)
+    got = _run(emu, p, planes, 0, hm, 0, sh, None, 1, H, 2)
+    assert np.isfinite(want).all()
+    assert np.array_equal(got, want), "max abs err %g" % np.abs(got - want).max()
+
+
 def test_many_items_per_cta_bit_exact(emu, orc):
     """One emulated CTA streams every item of the frame back to back (several chunks per strip, several strips): the rolling
     state and the rings run across item boundaries."""

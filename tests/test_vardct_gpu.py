@@ -102,6 +102,31 @@ def test_epf(recon, orc, iters):
         assert np.array_equal(g2, ref) if exact else np.abs(g2 - ref).max() <= 5e-6
 
 
+@pytest.mark.parametrize("iters", [1, 3])
+@pytest.mark.parametrize("stage2", ["stream", "tile", "staged"])
+def test_epf_with_non_positive_hf_multipliers(recon, orc, iters, stage2):
+    """HFMetadata takes the HF multiplier as 1 + a Modular-decoded value (HFMetadata.java:49): a crafted stream can make it zero or
+    negative, sigma and 1/sigma then are infinite or negative and epfWeight's 1 - x exceeds 1.  Every stage-2 kernel must still follow
+    the reference (the stream kernel clamps with a saturating subtract only in rows whose 1/sigma are all non-negative)."""
+    W, H = 328, 200
+    p = default_frame_params(W, H, epf_iters=iters)
+    rng = np.random.default_rng(40 + iters)
+    planes = (rng.random((3, H, W), dtype=np.float32) * np.array([0.05, 1.0, 1.0], np.float32)[:, None, None]) * 0.2 + 0.4
+    hm = rng.integers(1, 5, size=(H // 8, W // 8)).astype(np.int32)
+    sh = rng.integers(0, 8, size=(H // 8, W // 8)).astype(np.int32)
+    hm[rng.random(hm.shape) < 0.2] = -3
+    hm[rng.random(hm.shape) < 0.1] = 0
+    sh[(hm < 0) & (sh == 0)] = 5          # sharpness 0 with a negative multiplier (1/sigma = -inf) breeds NaNs: out of this test's scope
+    ref = orc.epf(p, planes, hm, sh, nthreads=8)
+    assert np.isfinite(ref).all()
+    recon.set_option(_lib.OPT_STAGE2, {"stream": _lib.STAGE2_STREAM, "tile": _lib.STAGE2_TILE, "staged": _lib.STAGE2_STAGED}[stage2])
+    try:
+        got = recon.performEdgePreservingFilter(p, planes, hm, sh)
+    finally:
+        recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
+    assert np.array_equal(got, ref), "max abs err %g" % np.abs(got - ref).max()
+
+
 def test_epf_rejects_bad_sharpness(recon):
     p = default_frame_params(64, 64, epf_iters=1)
     planes = np.zeros((3, 64, 64), np.float32)

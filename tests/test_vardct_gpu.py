@@ -127,6 +127,31 @@ def test_epf_with_non_positive_hf_multipliers(recon, orc, iters, stage2):
     assert np.array_equal(got, ref), "max abs err %g" % np.abs(got - ref).max()
 
 
+def test_stream_kernel_random_shapes(recon):
+    """The stream kernel (forced) against the staged kernels on thirty random frame shapes and filter settings, through the whole
+    reconstruction: widths from one 8-pixel block to several column strips with a ragged last strip, heights from one block row to several
+    chunks, every (gab, epf_iters >= 1).  The staged kernels are the simple form the fused ones are checked against; they are held to the
+    oracle elsewhere in this file."""
+    rng = np.random.default_rng(20261017)
+    qw, qo = qm_generate()
+    recon.setWeights(qw, qo)
+    for k in range(30):
+        W = 8 * int(rng.integers(1, 64)) if k % 4 else 8 * int(rng.integers(100, 170))
+        H = 8 * int(rng.integers(1, 48)) if k % 5 else 8 * int(rng.integers(60, 100))
+        iters, gab = int(rng.integers(1, 4)), bool(rng.integers(0, 2))
+        p = default_frame_params(W, H, epf_iters=iters, gab=gab)
+        st = synth.make_state(W, H, seed=7000 + k, params=p, qm_weights=qw, qm_offsets=qo)
+        out = {}
+        for name, opt in (("stream", _lib.STAGE2_STREAM), ("staged", _lib.STAGE2_STAGED)):
+            recon.set_option(_lib.OPT_STAGE2, opt)
+            try:
+                out[name] = recon.reconstruct(p, st)
+            finally:
+                recon.set_option(_lib.OPT_STAGE2, _lib.STAGE2_AUTO)
+        assert np.array_equal(out["stream"], out["staged"]), "%dx%d gab %d epf %d: max abs diff %g" % (
+            W, H, gab, iters, np.abs(out["stream"] - out["staged"]).max())
+
+
 def test_epf_rejects_bad_sharpness(recon):
     p = default_frame_params(64, 64, epf_iters=1)
     planes = np.zeros((3, 64, 64), np.float32)

@@ -69,8 +69,8 @@ __device__ __forceinline__ float k2s_subsat(float a, float b) { float r; asm("su
 #define K2S_PITCH 128         /* floats per ring row: 32 lanes x 4 */
 #ifndef K2S_BAND
 #define K2S_BAND 16           /* rows per tick = warps per CTA: one row (or one pair of map rows) per warp and phase.  16: one CTA per SM
-                                 (8K frame, stage 2: 1.52 ms); 8: two CTAs of 8 warps per SM, one computes while the other sits at a
-                                 barrier (1.55 ms: the barriers are not what limits it) */
+                                 (8K frame, stage 2: 1.32 ms); 8: two CTAs of 8 warps per SM, one computes while the other sits at a
+                                 barrier (no faster: the barriers are not what limits it); 18: 18 warps at 96 registers (1.52 ms) */
 #endif
 #define K2S_NWARPS K2S_BAND
 #define K2S_CTAS_PER_SM (K2S_BAND == 8 ? 2 : 1)
@@ -80,7 +80,8 @@ __device__ __forceinline__ float k2s_subsat(float a, float b) { float r; asm("su
 //   GAB: G -2, W0 -6 reads 2 above -> BAND + 6      D0 maps: D0 -6, W0 -6 reads 2 above -> BAND + 2
 //   P0:  W0 -6, D1 / W1 -8 read 1 above -> BAND + 3  D1 maps: D1 -8, W1 -8 reads 1 above -> BAND + 1
 //   P1:  W1 -8, P2 -9 reads 1 above -> BAND + 2      RAW: next band's loads are issued after G; G -2 reads 1 above -> BAND + 3, in boxes of 4
-#define K2S_RS_RAW ((K2S_BAND + 3 + 3) & ~3)
+#define K2S_BOX (K2S_BAND % 4 == 0 ? 4 : 2)      /* rows per TMA box: divides the band and the 8-row granularity of the items */
+#define K2S_RS_RAW ((K2S_BAND + 3 + K2S_BOX - 1) / K2S_BOX * K2S_BOX)
 #define K2S_RS_GAB (K2S_BAND + 6)
 #define K2S_RS_P0 (K2S_BAND + 3)
 #define K2S_RS_P1 (K2S_BAND + 2)
@@ -154,7 +155,7 @@ K2S_FN void k2s_st4(float *p, K2SQuad q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p
 K2S_FN void k2s_stg4(float *p, K2SQuad q) { p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
 // a 128 x 4 box at (x, y): zero fill outside the tensor, exactly what the TMA unit writes
 K2S_FN void k2s_tma_box(float *dst, const K2STmap &m, int x, int y) {
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < K2S_BOX; r++)
         for (int i = 0; i < K2S_PITCH; i++) {
             const int yy = y + r, xx = x + i;
             dst[r * K2S_PITCH + i] = (yy >= 0 && yy < m.rows && xx >= 0 && xx < m.w) ? m.base[(long long)yy * m.pitch + xx] : 0.0f;
@@ -811,17 +812,17 @@ K2S_FN int k2s_total_rows(const K2SArgs &A) {
 // two).  One thread issues; the slots were last read by G in tick t - 1, which a CTA barrier separates from this call.
 K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int t, int total,
                               K2SCursor &cur) {
-    int boxes = (total - K2S_BAND * t + 3) >> 2;
+    int boxes = (total - K2S_BAND * t + K2S_BOX - 1) / K2S_BOX;
     if (boxes <= 0) return;
-    if (boxes > K2S_BAND / 4) boxes = K2S_BAND / 4;
+    if (boxes > K2S_BAND / K2S_BOX) boxes = K2S_BAND / K2S_BOX;
 #ifndef K2S_HOST_EMU
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of tick t - 1 before async-proxy writes
     uint64_t *bar = bars + (t & 1);
-    k2s_mbar_expect_tx(bar, boxes * 3 * 4 * K2S_PITCH * 4);
+    k2s_mbar_expect_tx(bar, boxes * 3 * K2S_BOX * K2S_PITCH * 4);
 #endif
 #pragma unroll 1
     for (int h = 0; h < boxes; h++) {
-        const int S = K2S_BAND * t + 4 * h;
+        const int S = K2S_BAND * t + K2S_BOX * h;
         const K2SRow R = k2s_at(A, cur, S);       // the issuing thread's warp is on the phase's critical path: no divisions here
         const int ty = R.z * A.P.rows + R.y + A.tma_row0, slot = k2s_slot(S, K2S_RS_RAW);
         float *dst = sm + K2S_OFF_RAW + slot * K2S_PITCH;
@@ -920,7 +921,7 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
         if (ITERS == 3) {
             // ---- D0: 6 maps x BAND / 2 row pairs; a warp forms three maps of its row pair at once (they read the same input rows) ----
             {
-                const int S0 = S16 + Cfg::D0 + 2 * (warp & (K2S_BAND / 2 - 1));
+                const int S0 = S16 + Cfg::D0 + 2 * (warp % (K2S_BAND / 2));
                 if (S0 + 1 >= 0 && S0 < total) {
                     if (warp < K2S_BAND / 2) k2s_d_triple<0>(A.P, gab, d0, S0, lane);
                     else k2s_d_triple<1>(A.P, gab, d0, S0, lane);
@@ -940,7 +941,7 @@ K2S_FN void k2s_body(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM
         }
         // ---- D1: 2 maps x BAND / 2 row pairs ----
         {
-            const int S0 = S16 + Cfg::D1 + 2 * (warp & (K2S_BAND / 2 - 1));
+            const int S0 = S16 + Cfg::D1 + 2 * (warp % (K2S_BAND / 2));
             if (warp < K2S_BAND / 2) k2s_d_task<0, 1>(A, in1, RS1, d1, K2S_RS_D1, S0, total, lane);
             else k2s_d_task<1, 0>(A, in1, RS1, d1 + K2S_RS_D1 * K2S_PITCH, K2S_RS_D1, S0, total, lane);
         }
@@ -1066,7 +1067,7 @@ static inline int k2_stream_launch(const K2Params &K, const float *inv_sigma, cu
     for (int c = 0; c < 3; c++) {
         const cuuint64_t dims[2] = {(cuuint64_t)K.W, (cuuint64_t)map_rows};
         const cuuint64_t strides[1] = {(cuuint64_t)K.in_pitch * 4};
-        const cuuint32_t box[2] = {K2S_PITCH, 4}, es[2] = {1, 1};
+        const cuuint32_t box[2] = {K2S_PITCH, K2S_BOX}, es[2] = {1, 1};
         void *base = (void *)(K.in[c] - (K.has_top ? (long long)JXLB200_HALO_ROWS * K.in_pitch : 0));
         if (k2s_encoder()(&tm[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

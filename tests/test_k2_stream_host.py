@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HALO = 8
 
 
-@pytest.fixture(scope="module", params=["libk2stream_host.so", "libk2stream_host16.so"], ids=["band8", "band16"])
+@pytest.fixture(scope="module", params=["libk2stream_host.so", "libk2stream_host8.so", "libk2stream_host18.so"], ids=["band16", "band8", "band18"])
 def emu(request):
     subprocess.check_call(["make", "-C", os.path.join(HERE, "host")], stdout=subprocess.DEVNULL)
     L = C.CDLL(os.path.join(HERE, "host", request.param))

@@ -74,9 +74,9 @@ __device__ __forceinline__ float k2s_subsat(float a, float b) { float r; asm("su
 #endif
 #define K2S_NWARPS K2S_BAND
 #define K2S_CTAS_PER_SM (K2S_BAND == 8 ? 2 : 1)
-// Ring sizes in rows.  Within a tick the writer of a ring (first row of its band: 16t + bw) runs before its readers (16t + br, reading
+// Ring sizes in rows.  Within a tick the writer of a ring (first row of its band: BAND t + bw) runs before its readers (BAND t + br, reading
 // up to `a` rows above their own); when the writer's band lands, the readers of the same tick still need everything from row
-// 16t + br - a on, so a ring holds BAND + bw - br + a rows:
+// BAND t + br - a on, so a ring holds BAND + bw - br + a rows:
 //   GAB: G -2, W0 -6 reads 2 above -> BAND + 6      D0 maps: D0 -6, W0 -6 reads 2 above -> BAND + 2
 //   P0:  W0 -6, D1 / W1 -8 read 1 above -> BAND + 3  D1 maps: D1 -8, W1 -8 reads 1 above -> BAND + 1
 //   P1:  W1 -8, P2 -9 reads 1 above -> BAND + 2      RAW: next band's loads are issued after G; G -2 reads 1 above -> BAND + 3, in boxes of 4
@@ -232,7 +232,7 @@ K2S_FN K2SRow k2s_locate(const K2SArgs &A, int S) {
     r.y = chunk * A.ch - K2S_HALO + r.loc;
     return r;
 }
-// the divisions above are paid once per item, not once per row: a role keeps the item its last row was in
+// the divisions above are paid once per item, not once per row: a warp keeps the item its last row was in
 struct K2SCursor { int lo, hi, x0, z, y_lo, valid; };
 K2S_FN void k2s_cursor_init(K2SCursor &c) { c.lo = 0; c.hi = 0; c.x0 = 0; c.z = 0; c.y_lo = 0; c.valid = 0; }
 K2S_FN K2SRow k2s_at(const K2SArgs &A, K2SCursor &c, int S) {
@@ -808,8 +808,9 @@ K2S_FN int k2s_total_rows(const K2SArgs &A) {
     return mine * A.ir;
 }
 
-// rows [16t, 16t + 16) of the stream -> RAW ring: four 4-row boxes per plane (an item is a multiple of 8 rows, a box never straddles
-// two).  One thread issues; the slots were last read by G in tick t - 1, which a CTA barrier separates from this call.
+// rows [BAND t, BAND t + BAND) of the stream -> RAW ring: BAND / BOX boxes per plane (an item is a multiple of 8 rows, a box never
+// straddles two).  One thread issues (twelve lanes issuing at once were measured no faster); the slots were last read by G a tick ago,
+// which a CTA barrier separates from this call.
 K2S_FN void k2s_load_band(const K2SArgs &A, float *sm, uint64_t *bars, K2S_TMAP_PARAM t0, K2S_TMAP_PARAM t1, K2S_TMAP_PARAM t2, int t, int total,
                               K2SCursor &cur) {
     int boxes = (total - K2S_BAND * t + K2S_BOX - 1) / K2S_BOX;

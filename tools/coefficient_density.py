@@ -46,8 +46,8 @@ for name in ("lenna", "bbb", "sollevante-hdr", "ants", "bench"):
     a, b, area = stats(p.vardct_state(k))
     print("| `%s.jxl` | %.2f %% | %s | %.1f %% |" % (name, 100 * a, "%.2f %%" % (100 * b) if b is not None else "-", 100 * area))
     p.close()
-from oracle import oracle
-qw, qo = oracle.qm_default_weights()
+from jxlatte_b200.host import qm_generate      # the product library's tables (bit-identical to the checker's: tests/test_abi.py)
+qw, qo = qm_generate()
 for label, kw in (("synthetic default (amplitude-aware, the bench headline)", {}), ("synthetic, SURVEY 8(d) as written (`survey_spec=True`)", {"survey_spec": True})):
     pr = default_frame_params(2048, 2048, epf_iters=3)
     st = synth.make_state(2048, 2048, seed=synth.SEED_BASE + 2, params=pr, qm_weights=qw, qm_offsets=qo, **kw)

@@ -218,7 +218,12 @@ struct K2SRow {
     int loc;      // row inside the item, 0 .. ir-1 (8 .. 8+ch-1 are the rows the item produces)
     int valid;    // the CTA has such an item
 };
-K2S_FN K2SRow k2s_locate(const K2SArgs &A, int S) {
+#ifdef K2S_HOST_EMU
+#define K2S_COLD static inline
+#else
+#define K2S_COLD __device__ __noinline__      /* runs once per item and stage: kept out of line, every row function would carry a copy */
+#endif
+K2S_COLD K2SRow k2s_locate(const K2SArgs &A, int S) {
     K2SRow r;
     const int k = S / A.ir;
     r.loc = S - k * A.ir;
@@ -650,13 +655,17 @@ template <bool SAT> K2S_FN void k2s_w0_body(const K2SArgs &A, float *sm, const K
     }
     k2s_emit(P, ring, K2S_RS_P0, K2S_MARGIN_P0, R, S, lane, out);
 }
+// the literal-clamp forms run only for rows with a non-positive HF multiplier: out of line, away from the hot code
+K2S_COLD void k2s_w0_body_literal(const K2SArgs &A, float *sm, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
+    k2s_w0_body<false>(A, sm, R, S, lane, is, m);
+}
 K2S_FN int k2s_w0_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
     const K2SRow R = k2s_at(A, cur, S);
     const int kind = R.valid ? k2s_row_kind(A.P, R.y, K2S_MARGIN_P0) : 1;
     if (kind != 0) return kind;          // 2: a row below the frame, copied from behind after the phase's barrier (k2s_fixup)
     float m[4];
     const float is = k2s_sigma(A, R, lane, m);                           // a global load: issued before anything else of the row
-    if (k2s_any(is < 0.0f)) k2s_w0_body<false>(A, sm, R, S, lane, is, m);
+    if (k2s_any(is < 0.0f)) k2s_w0_body_literal(A, sm, R, S, lane, is, m);
     else k2s_w0_body<true>(A, sm, R, S, lane, is, m);
     return 0;
 }
@@ -716,13 +725,17 @@ K2S_FN void k2s_w1_body(const K2SArgs &A, float *sm, const float *in, const K2SR
     if (LAST) k2s_final(A, R, lane, out);
     else k2s_emit(P, ring, K2S_RS_P1, K2S_MARGIN_P1, R, S, lane, out);
 }
+template <int RS_IN, bool LAST>
+K2S_COLD void k2s_w1_body_literal(const K2SArgs &A, float *sm, const float *in, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
+    k2s_w1_body<RS_IN, LAST, false>(A, sm, in, R, S, lane, is, m);
+}
 template <int RS_IN, bool LAST> K2S_FN int k2s_w1_row(const K2SArgs &A, float *sm, const float *in, K2SCursor &cur, int S, int lane) {
     const K2SRow R = k2s_at(A, cur, S);
     const int kind = R.valid ? k2s_row_kind(A.P, R.y, LAST ? 0 : K2S_MARGIN_P1) : 1;
     if (kind != 0) return kind;
     float m[4];
     const float is = k2s_sigma(A, R, lane, m);
-    if (k2s_any(is < 0.0f)) k2s_w1_body<RS_IN, LAST, false>(A, sm, in, R, S, lane, is, m);
+    if (k2s_any(is < 0.0f)) k2s_w1_body_literal<RS_IN, LAST>(A, sm, in, R, S, lane, is, m);
     else k2s_w1_body<RS_IN, LAST, true>(A, sm, in, R, S, lane, is, m);
     return 0;
 }
@@ -790,12 +803,15 @@ template <bool SAT> K2S_FN void k2s_p2_body(const K2SArgs &A, float *sm, const K
     for (int c = 0; c < 3; c++) { out[c].x = o[c][0]; out[c].y = o[c][1]; out[c].z = o[c][2]; out[c].w = o[c][3]; }
     k2s_final(A, R, lane, out);
 }
+K2S_COLD void k2s_p2_body_literal(const K2SArgs &A, float *sm, const K2SRow &R, int S, int lane, float is, const float (&m)[4]) {
+    k2s_p2_body<false>(A, sm, R, S, lane, is, m);
+}
 K2S_FN void k2s_p2_row(const K2SArgs &A, float *sm, K2SCursor &cur, int S, int lane) {
     const K2SRow R = k2s_at(A, cur, S);
     if (!R.valid || k2s_row_kind(A.P, R.y, 0) != 0) return;
     float m[4];
     const float is = k2s_sigma(A, R, lane, m);
-    if (k2s_any(is < 0.0f)) k2s_p2_body<false>(A, sm, R, S, lane, is, m);
+    if (k2s_any(is < 0.0f)) k2s_p2_body_literal(A, sm, R, S, lane, is, m);
     else k2s_p2_body<true>(A, sm, R, S, lane, is, m);
 }
 

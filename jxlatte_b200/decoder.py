@@ -79,8 +79,9 @@ class CudaEngine:
 
     def __init__(self, device=0, allow_tolerance_mode=False):
         """allow_tolerance_mode: let JXLOptions(OUTPUT_PNG, 8) select the re-associated stage 2 (JXLB200_OPT_STAGE2 = 2).  OFF by
-        default: measured on B200 that kernel (k2_fused) is inside the tolerance but SLOWER than the bit-exact k2_exact (2.40 vs
-        1.79 ms per 8K frame, profiles/r2_exact_vs_fast.md), so there is nothing to buy with the error yet."""
+        default: measured on B200 that kernel (k2_fused) is inside the tolerance but SLOWER than the bit-exact kernels (2.40 ms per
+        8K frame with three EPF passes against 1.31 ms for k2_stream and 1.65 ms for k2_exact; 0.58 against 0.55 ms with one pass:
+        profiles/r2_exact_vs_fast.md), so there is nothing to buy with the error."""
         from . import host
         self._host = host
         self.rec = host.Reconstructor(device)
